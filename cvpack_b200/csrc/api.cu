@@ -1,0 +1,281 @@
+// extern "C" entry points of libcvpack_b200.so (see include/cvpack_b200.h).
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cvp {
+
+std::atomic<int64_t> g_launch_count{0};
+static thread_local std::string t_error;
+void set_error(const std::string& message) { t_error = message; }
+
+int pair_sum_create(const cvp_pair_sum_desc*, cvp_cv**);
+int centroid_pair_sum_create(const cvp_centroid_pair_sum_desc*, cvp_cv**);
+int rmsd_create(const cvp_rmsd_desc*, cvp_cv**);
+int gyration_create(const cvp_gyration_desc*, cvp_cv**);
+int bonded_create(const cvp_bonded_desc*, cvp_cv**);
+int effective_mass(int dtype, const void* grad, const double* masses, int64_t B, int64_t N,
+                   void* emass, cudaStream_t stream);
+int measure_fp32_peak(double* tflops);
+
+namespace {
+
+int prepare(cvp_cv* cv) {
+  int device = -1;
+  CVP_CUDA_CHECK(cudaGetDevice(&device));
+  if (cv->device == device) return CVP_OK;
+  if (cv->device != -1) {
+    set_error("this spec was uploaded to another device; build one spec per device");
+    return CVP_ERR_UNSUPPORTED;
+  }
+  cudaDeviceProp prop;
+  CVP_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("libcvpack_b200 is built for sm_100a only; device is sm_" +
+              std::to_string(prop.major) + std::to_string(prop.minor));
+    return CVP_ERR_NO_DEVICE;
+  }
+  int status = cv->upload();
+  if (status != CVP_OK) return status;
+  cv->device = device;
+  return CVP_OK;
+}
+
+size_t elem_size(int dtype) { return dtype == CVP_F32 ? 4 : 8; }
+
+int check_args(cvp_cv* cv, int dtype, const void* positions, int box_mode, int64_t B, int64_t N,
+               void* value) {
+  CVP_REQUIRE(cv != nullptr, "null spec");
+  CVP_REQUIRE(dtype == CVP_F32 || dtype == CVP_F64, "dtype must be CVP_F32 or CVP_F64");
+  CVP_REQUIRE(positions != nullptr && value != nullptr, "null positions or value buffer");
+  CVP_REQUIRE(B >= 0, "negative frame count");
+  CVP_REQUIRE(N == cv->num_atoms, "the batch has " + std::to_string(N) +
+                                      " atoms per frame but the spec was built for " +
+                                      std::to_string(cv->num_atoms));
+  CVP_REQUIRE(box_mode >= CVP_BOX_NONE && box_mode <= CVP_BOX_PER_FRAME, "bad box mode");
+  return CVP_OK;
+}
+
+// frames per run() call for a given workspace budget
+int64_t frames_per_chunk(cvp_cv* cv, int dtype, bool need_grad, int64_t B) {
+  size_t per_frame = std::max<size_t>(1, cv->workspace_per_frame(dtype, need_grad));
+  size_t fixed = cv->workspace_fixed(dtype);
+  int64_t budget = cv->workspace_limit > (int64_t)fixed ? cv->workspace_limit - (int64_t)fixed : 0;
+  int64_t frames = std::max<int64_t>(1, budget / (int64_t)per_frame);
+  frames = std::min(frames, cv->max_frames_per_run());
+  return std::min<int64_t>(frames, std::max<int64_t>(B, 1));
+}
+
+}  // namespace
+}  // namespace cvp
+
+using namespace cvp;
+
+extern "C" {
+
+int cvp_pair_sum_create(const cvp_pair_sum_desc* desc, cvp_cv** out) {
+  return pair_sum_create(desc, out);
+}
+int cvp_centroid_pair_sum_create(const cvp_centroid_pair_sum_desc* desc, cvp_cv** out) {
+  return centroid_pair_sum_create(desc, out);
+}
+int cvp_rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) { return rmsd_create(desc, out); }
+int cvp_gyration_create(const cvp_gyration_desc* desc, cvp_cv** out) {
+  return gyration_create(desc, out);
+}
+int cvp_bonded_create(const cvp_bonded_desc* desc, cvp_cv** out) { return bonded_create(desc, out); }
+
+int cvp_destroy(cvp_cv* cv) {
+  delete cv;
+  return CVP_OK;
+}
+
+int cvp_active_atoms(const cvp_cv* cv, int32_t* count, int32_t* atoms) {
+  CVP_REQUIRE(cv != nullptr && count != nullptr, "null argument");
+  *count = (int32_t)cv->active_atoms.size();
+  if (atoms != nullptr)
+    std::copy(cv->active_atoms.begin(), cv->active_atoms.end(), atoms);
+  return CVP_OK;
+}
+
+int cvp_evaluate(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
+                 int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,
+                 void* stream) {
+  int status = check_args(cv, dtype, positions, box_mode, num_frames, num_atoms, value);
+  if (status != CVP_OK) return status;
+  if (num_frames == 0) return CVP_OK;
+  if ((status = prepare(cv)) != CVP_OK) return status;
+  const bool need_grad = grad != nullptr;
+  const int64_t chunk = frames_per_chunk(cv, dtype, need_grad, num_frames);
+  const size_t bytes = cv->workspace_fixed(dtype) + (size_t)chunk * cv->workspace_per_frame(dtype, need_grad);
+  if (bytes > cv->workspace.bytes) {
+    // growing frees the old allocation: make sure nothing queued earlier still uses it
+    if (cv->workspace.ptr) CVP_CUDA_CHECK(cudaDeviceSynchronize());
+    if ((status = cv->workspace.reserve(bytes)) != CVP_OK) return status;
+  }
+  const size_t es = elem_size(dtype);
+  for (int64_t first = 0; first < num_frames; first += chunk) {
+    EvalArgs a;
+    a.dtype = dtype;
+    a.num_frames = std::min(chunk, num_frames - first);
+    a.num_atoms = num_atoms;
+    a.positions = static_cast<const char*>(positions) + (size_t)first * num_atoms * 3 * es;
+    a.box = box;
+    if (box != nullptr && box_mode == CVP_BOX_PER_FRAME)
+      a.box = static_cast<const char*>(box) + (size_t)first * 9 * es;
+    a.box_mode = box == nullptr ? CVP_BOX_NONE : box_mode;
+    a.value = static_cast<char*>(value) + (size_t)first * es;
+    a.grad = need_grad ? static_cast<char*>(grad) + (size_t)first * num_atoms * 3 * es : nullptr;
+    a.flags = flags;
+    a.stream = static_cast<cudaStream_t>(stream);
+    if ((status = cv->run(a, cv->workspace.ptr)) != CVP_OK) return status;
+  }
+  return CVP_OK;
+}
+
+// Host-buffer path: frames flow through H2D copy -> kernels -> D2H copy in chunks; two slots so the
+// copies of one chunk overlap the kernels of the other (copy engines in both directions + SMs).
+int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
+                      int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,
+                      int device) {
+  int status = check_args(cv, dtype, positions, box_mode, num_frames, num_atoms, value);
+  if (status != CVP_OK) return status;
+  CVP_REQUIRE((flags & CVP_FLAG_ACCUMULATE) == 0, "accumulate is not supported on the host path");
+  if (num_frames == 0) return CVP_OK;
+  CVP_CUDA_CHECK(cudaSetDevice(device));
+  const size_t es = elem_size(dtype);
+  const bool need_grad = grad != nullptr;
+  const size_t frame_bytes = (size_t)num_atoms * 3 * es;
+  // chunk: at most ~256 MiB of coordinates, at least 1 frame, and >= 4 chunks when possible
+  int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t(256) << 20) / frame_bytes));
+  chunk = std::min(chunk, std::max<int64_t>(1, (num_frames + 3) / 4));
+  constexpr int SLOTS = 2;
+  struct Slot {
+    void *pos = nullptr, *grad = nullptr, *value = nullptr, *box = nullptr;
+    cudaStream_t stream = nullptr;
+  } slot[SLOTS];
+  void* shared_box = nullptr;
+  auto cleanup = [&]() {
+    for (auto& s : slot) {
+      if (s.stream) cudaStreamSynchronize(s.stream);
+      cudaFree(s.pos);
+      cudaFree(s.grad);
+      cudaFree(s.value);
+      cudaFree(s.box);
+      if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(shared_box);
+  };
+#define CVP_HOST_CHECK(expr)                                                             \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      set_error(std::string(#expr) + " failed: " + cudaGetErrorString(e__));             \
+      cleanup();                                                                         \
+      return CVP_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+  const bool have_box = box != nullptr && box_mode != CVP_BOX_NONE;
+  if (have_box && box_mode == CVP_BOX_SHARED) {
+    CVP_HOST_CHECK(cudaMalloc(&shared_box, 9 * es));
+    CVP_HOST_CHECK(cudaMemcpy(shared_box, box, 9 * es, cudaMemcpyHostToDevice));
+  }
+  for (auto& s : slot) {
+    CVP_HOST_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CVP_HOST_CHECK(cudaMalloc(&s.pos, (size_t)chunk * frame_bytes));
+    if (need_grad) CVP_HOST_CHECK(cudaMalloc(&s.grad, (size_t)chunk * frame_bytes));
+    CVP_HOST_CHECK(cudaMalloc(&s.value, (size_t)chunk * es));
+    if (have_box && box_mode == CVP_BOX_PER_FRAME)
+      CVP_HOST_CHECK(cudaMalloc(&s.box, (size_t)chunk * 9 * es));
+  }
+  // the spec's workspace is shared by both slots: kernels of consecutive chunks are serialised by
+  // an event chain, copies are not
+  cudaEvent_t kernels_done[SLOTS] = {nullptr, nullptr};
+  for (auto& e : kernels_done) CVP_HOST_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  int64_t index = 0;
+  status = CVP_OK;
+  for (int64_t first = 0; first < num_frames && status == CVP_OK; first += chunk, ++index) {
+    Slot& s = slot[index % SLOTS];
+    const int64_t count = std::min(chunk, num_frames - first);
+    CVP_HOST_CHECK(cudaMemcpyAsync(s.pos, static_cast<const char*>(positions) + (size_t)first * frame_bytes,
+                                   (size_t)count * frame_bytes, cudaMemcpyHostToDevice, s.stream));
+    const void* dbox = shared_box;
+    if (s.box) {
+      CVP_HOST_CHECK(cudaMemcpyAsync(s.box, static_cast<const char*>(box) + (size_t)first * 9 * es,
+                                     (size_t)count * 9 * es, cudaMemcpyHostToDevice, s.stream));
+      dbox = s.box;
+    }
+    if (index > 0)
+      CVP_HOST_CHECK(cudaStreamWaitEvent(s.stream, kernels_done[(index - 1) % SLOTS], 0));
+    status = cvp_evaluate(cv, dtype, s.pos, dbox, have_box ? box_mode : CVP_BOX_NONE, count,
+                          num_atoms, s.value, s.grad, flags, s.stream);
+    if (status != CVP_OK) break;
+    CVP_HOST_CHECK(cudaEventRecord(kernels_done[index % SLOTS], s.stream));
+    CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(value) + (size_t)first * es, s.value,
+                                   (size_t)count * es, cudaMemcpyDeviceToHost, s.stream));
+    if (need_grad)
+      CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(grad) + (size_t)first * frame_bytes, s.grad,
+                                     (size_t)count * frame_bytes, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (auto& s : slot)
+    if (s.stream) cudaStreamSynchronize(s.stream);
+  for (auto& e : kernels_done)
+    if (e) cudaEventDestroy(e);
+  cudaError_t last = cudaGetLastError();
+  cleanup();
+  if (status == CVP_OK && last != cudaSuccess) {
+    set_error(std::string("host evaluation failed: ") + cudaGetErrorString(last));
+    return CVP_ERR_CUDA;
+  }
+  return status;
+#undef CVP_HOST_CHECK
+}
+
+int cvp_effective_mass(int dtype, const void* grad, const double* masses, int64_t num_frames,
+                       int64_t num_atoms, void* emass, void* stream) {
+  CVP_REQUIRE(dtype == CVP_F32 || dtype == CVP_F64, "dtype must be CVP_F32 or CVP_F64");
+  CVP_REQUIRE(grad != nullptr && masses != nullptr && emass != nullptr, "null argument");
+  if (num_frames == 0) return CVP_OK;
+  return effective_mass(dtype, grad, masses, num_frames, num_atoms, emass,
+                        static_cast<cudaStream_t>(stream));
+}
+
+const char* cvp_last_error(void) { return t_error.c_str(); }
+int cvp_version(void) { return 100; }
+
+int cvp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    set_error("no CUDA device " + std::to_string(device));
+    return CVP_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  CVP_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return CVP_OK;
+}
+
+int64_t cvp_launch_count(void) { return g_launch_count.load(); }
+
+int cvp_set_workspace_limit(cvp_cv* cv, int64_t bytes) {
+  CVP_REQUIRE(cv != nullptr && bytes > 0, "bad workspace limit");
+  cv->workspace_limit = bytes;
+  return CVP_OK;
+}
+
+int cvp_set_option(cvp_cv* cv, const char* name, int value) {
+  CVP_REQUIRE(cv != nullptr && name != nullptr, "null argument");
+  return cv->set_option(name, value);
+}
+
+int cvp_measure_fp32_peak(int device, double* tflops) {
+  CVP_REQUIRE(tflops != nullptr, "null argument");
+  CVP_CUDA_CHECK(cudaSetDevice(device));
+  return measure_fp32_peak(tflops);
+}
+
+}  // extern "C"

@@ -1,0 +1,365 @@
+// Shared device/host helpers of the cvpack_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <type_traits>
+#include <utility>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cvpack_b200.h"
+
+namespace cvp {
+
+// ---- errors ------------------------------------------------------------------------------------
+void set_error(const std::string& message);
+extern std::atomic<int64_t> g_launch_count;
+
+#define CVP_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t cvp_err__ = (expr);                                                               \
+    if (cvp_err__ != cudaSuccess) {                                                               \
+      ::cvp::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(cvp_err__));         \
+      return CVP_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define CVP_REQUIRE(cond, message)                                                                \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      ::cvp::set_error(message);                                                                  \
+      return CVP_ERR_INVALID;                                                                     \
+    }                                                                                             \
+  } while (0)
+
+#define CVP_LAUNCH_CHECK()                                                                        \
+  do {                                                                                            \
+    ::cvp::g_launch_count.fetch_add(1, std::memory_order_relaxed);                                \
+    CVP_CUDA_CHECK(cudaGetLastError());                                                           \
+  } while (0)
+
+// ---- device buffers ----------------------------------------------------------------------------
+// Growable device allocation owned by a spec.
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t want) {
+    if (want <= bytes) return CVP_OK;
+    if (ptr) CVP_CUDA_CHECK(cudaFree(ptr));
+    ptr = nullptr;
+    bytes = 0;
+    CVP_CUDA_CHECK(cudaMalloc(&ptr, want));
+    bytes = want;
+    return CVP_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
+template <typename U>
+int upload(DeviceBuffer& buffer, const std::vector<U>& host) {
+  size_t bytes = host.size() * sizeof(U);
+  int status = buffer.reserve(bytes ? bytes : sizeof(U));
+  if (status != CVP_OK) return status;
+  if (bytes) CVP_CUDA_CHECK(cudaMemcpy(buffer.ptr, host.data(), bytes, cudaMemcpyHostToDevice));
+  return CVP_OK;
+}
+
+// Linear carve-up of a workspace allocation (256-byte aligned pieces).
+struct Carver {
+  char* base;
+  size_t offset = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename U>
+  U* take(size_t count) {
+    U* result = reinterpret_cast<U*>(base + offset);
+    offset += (count * sizeof(U) + 255) & ~size_t(255);
+    return result;
+  }
+};
+inline size_t carve_bytes(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
+
+// ---- the opaque spec ---------------------------------------------------------------------------
+struct EvalArgs {
+  int dtype;
+  const void* positions;  // device [B][N][3]
+  const void* box;        // device [9] or [B][9] or null
+  int box_mode;
+  int64_t num_frames;
+  int64_t num_atoms;
+  void* value;  // device [B]
+  void* grad;   // device [B][N][3] or null
+  int flags;
+  cudaStream_t stream;
+};
+
+}  // namespace cvp
+
+struct cvp_cv {
+  int num_atoms = 0;
+  int device = -1;  // device the spec's arrays live on (-1: not uploaded yet)
+  int64_t workspace_limit = int64_t(1) << 30;
+  std::vector<int32_t> active_atoms;  // sorted, unique
+  cvp::DeviceBuffer workspace;
+  virtual ~cvp_cv() { workspace.release(); }
+  // Upload index/parameter arrays to the current device.
+  virtual int upload() = 0;
+  // Workspace bytes needed per frame and independent of the frame count.
+  virtual size_t workspace_per_frame(int dtype, bool need_grad) const = 0;
+  virtual size_t workspace_fixed(int dtype) const { return 0; }
+  // Largest number of frames a single run() may be given.
+  virtual int64_t max_frames_per_run() const { return 1 << 20; }
+  // Evaluate frames [0, args.num_frames) of the given (already offset) pointers.
+  virtual int run(const cvp::EvalArgs& args, void* workspace) = 0;
+  virtual int set_option(const char* name, int value) {
+    (void)name;
+    (void)value;
+    return -1;
+  }
+};
+
+namespace cvp {
+
+// ---- device math -------------------------------------------------------------------------------
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  using type = float4;
+};
+template <>
+struct Vec4<double> {
+  using type = double4;
+};
+
+template <typename T>
+__device__ __forceinline__ T rsqrt_t(T x);
+template <>
+__device__ __forceinline__ float rsqrt_t<float>(float x) {
+  return rsqrtf(x);
+}
+template <>
+__device__ __forceinline__ double rsqrt_t<double>(double x) {
+  return 1.0 / sqrt(x);
+}
+template <typename T>
+__device__ __forceinline__ T sqrt_t(T x);
+template <>
+__device__ __forceinline__ float sqrt_t<float>(float x) {
+  return sqrtf(x);
+}
+template <>
+__device__ __forceinline__ double sqrt_t<double>(double x) {
+  return sqrt(x);
+}
+template <typename T>
+__device__ __forceinline__ T rint_t(T x);
+template <>
+__device__ __forceinline__ float rint_t<float>(float x) {
+  return rintf(x);
+}
+template <>
+__device__ __forceinline__ double rint_t<double>(double x) {
+  return rint(x);
+}
+
+// x^n for a non-negative integer n (exact same multiplication tree on host oracle is not needed:
+// results are compared within floating-point tolerance).
+template <typename T>
+__device__ __forceinline__ T powi(T x, int n) {
+  T result = T(1);
+  T base = x;
+  while (n > 0) {
+    if (n & 1) result *= base;
+    base *= base;
+    n >>= 1;
+  }
+  return result;
+}
+
+// Periodic box of one frame, OpenMM reduced form: a=(ax,0,0) b=(bx,by,0) c=(cx,cy,cz).
+template <typename T>
+struct Box {
+  T ax, bx, by, cx, cy, cz;
+  T inv_ax, inv_by, inv_cz;
+};
+
+template <typename T>
+__device__ __forceinline__ Box<T> load_box(const T* box, int box_mode, int64_t frame) {
+  Box<T> result;
+  const T* p = box + (box_mode == CVP_BOX_PER_FRAME ? frame * 9 : 0);
+  result.ax = p[0];
+  result.bx = p[3];
+  result.by = p[4];
+  result.cx = p[6];
+  result.cy = p[7];
+  result.cz = p[8];
+  result.inv_ax = T(1) / result.ax;
+  result.inv_by = T(1) / result.by;
+  result.inv_cz = T(1) / result.cz;
+  return result;
+}
+
+// Minimum-image displacement.  MODE 0: none, 1: rectangular box, 2: triclinic (reduce along c,
+// then b, then a -- the order OpenMM's ReferenceForce::getDeltaRPeriodicTriclinic uses).
+template <int MODE, typename T>
+__device__ __forceinline__ void min_image(T& dx, T& dy, T& dz, const Box<T>& box) {
+  if (MODE == 1) {
+    dx -= box.ax * rint_t(dx * box.inv_ax);
+    dy -= box.by * rint_t(dy * box.inv_by);
+    dz -= box.cz * rint_t(dz * box.inv_cz);
+  } else if (MODE == 2) {
+    T s = rint_t(dz * box.inv_cz);
+    dx -= s * box.cx;
+    dy -= s * box.cy;
+    dz -= s * box.cz;
+    s = rint_t(dy * box.inv_by);
+    dx -= s * box.bx;
+    dy -= s * box.by;
+    s = rint_t(dx * box.inv_ax);
+    dx -= s * box.ax;
+  }
+}
+
+// ---- reductions --------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int offset = 16; offset > 0; offset >>= 1) v += __shfl_xor_sync(0xffffffffu, v, offset);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int offset = 16; offset > 0; offset >>= 1) v += __shfl_xor_sync(0xffffffffu, v, offset);
+  return v;
+}
+
+// Deterministic block sum of K doubles per thread; result valid in thread 0.  `scratch` must hold
+// K * (blockDim.x/32) doubles.  All threads must call.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* scratch) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int num_warps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();  // scratch may still be in use from a previous call
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scratch[k * num_warps + warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x = lane < num_warps ? scratch[k * num_warps + lane] : 0.0;
+      v[k] = warp_sum(x);
+    }
+  }
+}
+
+// ---- step functions S(x) -----------------------------------------------------------------------
+struct StepParams {
+  int kind;
+  int n;  // exponent n (p0)
+  int m;  // exponent m (p1), CVP_STEP_PLUMED only
+};
+
+// S(x) and dS/dx for x >= 0.
+template <typename T>
+__device__ __forceinline__ void step_function(const StepParams& p, T x, T& s, T& ds) {
+  switch (p.kind) {
+    case CVP_STEP_RATIONAL: {
+      T xn1 = powi(x, p.n - 1);
+      T inv = T(1) / (T(1) + xn1 * x);
+      s = inv;
+      ds = -T(p.n) * xn1 * inv * inv;
+      break;
+    }
+    case CVP_STEP_HEAVISIDE: {
+      s = x <= T(1) ? T(1) : T(0);
+      ds = T(0);
+      break;
+    }
+    case CVP_STEP_RATIONAL_PAIR: {
+      T xn1 = powi(x, p.n - 1);
+      T xn = xn1 * x;
+      T num = T(1) + xn;
+      T den = num + xn * xn;
+      T inv = T(1) / den;
+      s = num * inv;
+      // d/dx [num/den] = (num' den - num den')/den^2, num' = n x^(n-1), den' = num' (1 + 2 x^n)
+      T dnum = T(p.n) * xn1;
+      ds = (dnum * den - num * dnum * (T(1) + T(2) * xn)) * inv * inv;
+      break;
+    }
+    default: {  // CVP_STEP_PLUMED
+      T xn1 = powi(x, p.n - 1), xm1 = powi(x, p.m - 1);
+      T num = T(1) - xn1 * x, den = T(1) - xm1 * x;
+      if (fabs((double)den) < 1e-6) {
+        // removable singularity at x = 1: Taylor expansion to first order
+        T r = T(p.n) / T(p.m);
+        s = r * (T(1) + T(0.5) * T(p.n - p.m) * (x - T(1)));
+        ds = r * T(0.5) * T(p.n - p.m);
+      } else {
+        T inv = T(1) / den;
+        s = num * inv;
+        ds = (-T(p.n) * xn1 * den + num * T(p.m) * xm1) * inv * inv;
+      }
+      break;
+    }
+  }
+}
+
+// ---- TMA (bulk async copy) + mbarrier, raw PTX -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy (UBLKCP); bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_addr(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+      : "memory");
+}
+
+inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace cvp

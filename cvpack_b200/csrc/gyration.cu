@@ -1,0 +1,313 @@
+// Radius of gyration (and its square) of an atom group, value + gradient, for a batch of frames.
+//
+// Replaces the CustomCentroidBondForce constructions of cvpack/radius_of_gyration.py:85-92 and
+// radius_of_gyration_sq.py:87-89 (base_radius_of_gyration.py:22-37):
+//   rg^2 = (1/n) sum_i |d_i|^2,  d_i = r_i - c  (minimum image if periodic),  c = sum_i w_i r_i
+//   d rg^2/d r_k = (2/n) [ d_k - w_k sum_i d_i ],   d rg = d rg^2 / (2 rg)
+// Streaming, HBM-bound: coordinates are read once per pass, sums are carried in double (the
+// single-pass identity sum|r-c|^2 = sum|r|^2 - 2 c.sum r + n|c|^2 cancels badly in float).
+#include "common.cuh"
+
+namespace cvp {
+namespace {
+
+constexpr int GYR_THREADS = 256;
+constexpr int GYR_ATOMS_PER_BLOCK = 4096;
+
+// pass 1: per-(frame, slice) partial sums {sum w r (3), sum r (3), sum |r|^2}
+template <typename T>
+__global__ void __launch_bounds__(GYR_THREADS)
+    gyration_sums_kernel(const T* __restrict__ pos, int64_t num_atoms,
+                         const int32_t* __restrict__ group, const double* __restrict__ weights,
+                         int n, int first_atom, int nslice, double* __restrict__ partials) {
+  __shared__ double scratch[7 * (GYR_THREADS / 32)];
+  const int64_t b = blockIdx.x / nslice;
+  const int slice = blockIdx.x - (int)b * nslice;
+  const int begin = slice * GYR_ATOMS_PER_BLOCK;
+  const int end = min(n, begin + GYR_ATOMS_PER_BLOCK);
+  const T* frame = pos + b * num_atoms * 3;
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = begin + threadIdx.x; i < end; i += GYR_THREADS) {
+    const int atom = group ? group[i] : first_atom + i;
+    const double x = frame[3 * (int64_t)atom], y = frame[3 * (int64_t)atom + 1],
+                 z = frame[3 * (int64_t)atom + 2];
+    const double w = weights[i];
+    v[0] += w * x;
+    v[1] += w * y;
+    v[2] += w * z;
+    v[3] += x;
+    v[4] += y;
+    v[5] += z;
+    v[6] += x * x + y * y + z * z;
+  }
+  block_sum<7>(v, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) partials[((size_t)b * nslice + slice) * 7 + k] = v[k];
+  }
+}
+
+// Per-frame record shared by the later passes.
+struct GyrationFrame {
+  double c[3];     // centre
+  double s[3];     // sum_i d_i
+  double rg2;      // squared radius of gyration
+  double factor;   // gradient prefactor: 2/n (squared) or 1/(n rg)
+};
+
+// pass 2 (one warp per frame): centre; non-periodic value.
+template <typename T>
+__global__ void gyration_centre_kernel(const double* __restrict__ partials, int nslice, int n,
+                                       int periodic, int squared, GyrationFrame* __restrict__ rec,
+                                       T* __restrict__ value, int accumulate, int64_t num_frames) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (b >= num_frames) return;
+  double sum[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    double v = 0.0;
+    for (int s = lane; s < nslice; s += 32) v += partials[((size_t)b * nslice + s) * 7 + k];
+    sum[k] = warp_sum(v);
+  }
+  if (lane != 0) return;
+  GyrationFrame r;
+  r.c[0] = sum[0];
+  r.c[1] = sum[1];
+  r.c[2] = sum[2];
+  if (!periodic) {
+    double cc = r.c[0] * r.c[0] + r.c[1] * r.c[1] + r.c[2] * r.c[2];
+    double cs = r.c[0] * sum[3] + r.c[1] * sum[4] + r.c[2] * sum[5];
+    r.rg2 = fmax(0.0, (sum[6] - 2.0 * cs + n * cc) / n);
+    r.s[0] = sum[3] - n * r.c[0];
+    r.s[1] = sum[4] - n * r.c[1];
+    r.s[2] = sum[5] - n * r.c[2];
+    double rg = sqrt(r.rg2);
+    r.factor = squared ? 2.0 / n : (rg > 0.0 ? 1.0 / (n * rg) : 0.0);
+    double result = squared ? r.rg2 : rg;
+    value[b] = accumulate ? T((double)value[b] + result) : T(result);
+  }
+  rec[b] = r;
+}
+
+// pass 3 (periodic only): partial sums {sum d (3), sum |d|^2} with d = minimum image of r - c
+template <typename T, int PBC>
+__global__ void __launch_bounds__(GYR_THREADS)
+    gyration_periodic_sums_kernel(const T* __restrict__ pos, int64_t num_atoms,
+                                  const int32_t* __restrict__ group, int n, int first_atom,
+                                  int nslice, const T* __restrict__ box, int box_mode,
+                                  const GyrationFrame* __restrict__ rec,
+                                  double* __restrict__ partials) {
+  __shared__ double scratch[4 * (GYR_THREADS / 32)];
+  const int64_t b = blockIdx.x / nslice;
+  const int slice = blockIdx.x - (int)b * nslice;
+  const int begin = slice * GYR_ATOMS_PER_BLOCK;
+  const int end = min(n, begin + GYR_ATOMS_PER_BLOCK);
+  const T* frame = pos + b * num_atoms * 3;
+  const Box<double> bx = [&] {
+    Box<T> t = load_box(box, box_mode, b);
+    Box<double> d;
+    d.ax = t.ax; d.bx = t.bx; d.by = t.by; d.cx = t.cx; d.cy = t.cy; d.cz = t.cz;
+    d.inv_ax = 1.0 / d.ax; d.inv_by = 1.0 / d.by; d.inv_cz = 1.0 / d.cz;
+    return d;
+  }();
+  const double cx = rec[b].c[0], cy = rec[b].c[1], cz = rec[b].c[2];
+  double v[4] = {0, 0, 0, 0};
+  for (int i = begin + threadIdx.x; i < end; i += GYR_THREADS) {
+    const int atom = group ? group[i] : first_atom + i;
+    double dx = frame[3 * (int64_t)atom] - cx, dy = frame[3 * (int64_t)atom + 1] - cy,
+           dz = frame[3 * (int64_t)atom + 2] - cz;
+    min_image<PBC>(dx, dy, dz, bx);
+    v[0] += dx;
+    v[1] += dy;
+    v[2] += dz;
+    v[3] += dx * dx + dy * dy + dz * dz;
+  }
+  block_sum<4>(v, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) partials[((size_t)b * nslice + slice) * 4 + k] = v[k];
+  }
+}
+
+template <typename T>
+__global__ void gyration_periodic_finish_kernel(const double* __restrict__ partials, int nslice,
+                                                int n, int squared, GyrationFrame* __restrict__ rec,
+                                                T* __restrict__ value, int accumulate,
+                                                int64_t num_frames) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (b >= num_frames) return;
+  double sum[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = 0.0;
+    for (int s = lane; s < nslice; s += 32) v += partials[((size_t)b * nslice + s) * 4 + k];
+    sum[k] = warp_sum(v);
+  }
+  if (lane != 0) return;
+  GyrationFrame r = rec[b];
+  r.s[0] = sum[0];
+  r.s[1] = sum[1];
+  r.s[2] = sum[2];
+  r.rg2 = sum[3] / n;
+  double rg = sqrt(r.rg2);
+  r.factor = squared ? 2.0 / n : (rg > 0.0 ? 1.0 / (n * rg) : 0.0);
+  double result = squared ? r.rg2 : rg;
+  value[b] = accumulate ? T((double)value[b] + result) : T(result);
+  rec[b] = r;
+}
+
+// gradient pass: g_k = factor * (d_k - w_k S)
+template <typename T, int PBC>
+__global__ void __launch_bounds__(GYR_THREADS)
+    gyration_gradient_kernel(const T* __restrict__ pos, int64_t num_atoms,
+                             const int32_t* __restrict__ group, const double* __restrict__ weights,
+                             int n, int first_atom, int nslice, const T* __restrict__ box,
+                             int box_mode, const GyrationFrame* __restrict__ rec,
+                             T* __restrict__ grad, int accumulate) {
+  const int64_t b = blockIdx.x / nslice;
+  const int slice = blockIdx.x - (int)b * nslice;
+  const int begin = slice * GYR_ATOMS_PER_BLOCK;
+  const int end = min(n, begin + GYR_ATOMS_PER_BLOCK);
+  const T* frame = pos + b * num_atoms * 3;
+  T* gframe = grad + b * num_atoms * 3;
+  Box<double> bx;
+  if (PBC != 0) {
+    Box<T> t = load_box(box, box_mode, b);
+    bx.ax = t.ax; bx.bx = t.bx; bx.by = t.by; bx.cx = t.cx; bx.cy = t.cy; bx.cz = t.cz;
+    bx.inv_ax = 1.0 / bx.ax; bx.inv_by = 1.0 / bx.by; bx.inv_cz = 1.0 / bx.cz;
+  }
+  const GyrationFrame r = rec[b];
+  for (int i = begin + threadIdx.x; i < end; i += GYR_THREADS) {
+    const int64_t atom = group ? group[i] : first_atom + i;
+    double dx = frame[3 * atom] - r.c[0], dy = frame[3 * atom + 1] - r.c[1],
+           dz = frame[3 * atom + 2] - r.c[2];
+    min_image<PBC>(dx, dy, dz, bx);
+    const double w = weights[i];
+    const double gx = r.factor * (dx - w * r.s[0]);
+    const double gy = r.factor * (dy - w * r.s[1]);
+    const double gz = r.factor * (dz - w * r.s[2]);
+    if (accumulate) {
+      gframe[3 * atom] += T(gx);
+      gframe[3 * atom + 1] += T(gy);
+      gframe[3 * atom + 2] += T(gz);
+    } else {
+      gframe[3 * atom] = T(gx);
+      gframe[3 * atom + 1] = T(gy);
+      gframe[3 * atom + 2] = T(gz);
+    }
+  }
+}
+
+struct GyrationCV : cvp_cv {
+  std::vector<int32_t> group;
+  std::vector<double> weights;
+  int periodic = 0, squared = 0;
+  bool contiguous = false;
+  DeviceBuffer d_group, d_weights;
+  ~GyrationCV() override {
+    d_group.release();
+    d_weights.release();
+  }
+  int upload() override {
+    int status = cvp::upload(d_group, group);
+    if (status != CVP_OK) return status;
+    return cvp::upload(d_weights, weights);
+  }
+  int nslice() const { return (int)div_up((int64_t)group.size(), GYR_ATOMS_PER_BLOCK); }
+  size_t workspace_per_frame(int, bool) const override {
+    return (size_t)nslice() * 7 * sizeof(double) + sizeof(GyrationFrame) + 64;
+  }
+  size_t workspace_fixed(int) const override { return 4 * 256; }
+  int64_t max_frames_per_run() const override {
+    return std::max<int64_t>(1, (int64_t(1) << 31) / nslice() - 1);
+  }
+
+  template <typename T, int PBC>
+  int run_impl(const EvalArgs& a, void* ws) {
+    const int64_t B = a.num_frames, N = a.num_atoms;
+    const int n = (int)group.size();
+    const int ns = nslice();
+    const bool accumulate = (a.flags & CVP_FLAG_ACCUMULATE) != 0;
+    const T* pos = static_cast<const T*>(a.positions);
+    const T* box = static_cast<const T*>(a.box);
+    T* value = static_cast<T*>(a.value);
+    T* grad = static_cast<T*>(a.grad);
+    cudaStream_t st = a.stream;
+    Carver carve(ws);
+    double* partials = carve.take<double>((size_t)B * ns * 7);
+    GyrationFrame* rec = carve.take<GyrationFrame>((size_t)B);
+    const int32_t* idx = contiguous ? nullptr : static_cast<const int32_t*>(d_group.ptr);
+    const double* w = static_cast<const double*>(d_weights.ptr);
+    const int first = group.front();
+    const unsigned grid = (unsigned)(B * ns);
+    const int warp_blocks = (int)div_up(B * 32, 128);
+
+    gyration_sums_kernel<T><<<grid, GYR_THREADS, 0, st>>>(pos, N, idx, w, n, first, ns, partials);
+    CVP_LAUNCH_CHECK();
+    gyration_centre_kernel<T><<<warp_blocks, 128, 0, st>>>(partials, ns, n, PBC != 0, squared, rec,
+                                                            value, accumulate ? 1 : 0, B);
+    CVP_LAUNCH_CHECK();
+    if (PBC != 0) {
+      gyration_periodic_sums_kernel<T, PBC><<<grid, GYR_THREADS, 0, st>>>(
+          pos, N, idx, n, first, ns, box, a.box_mode, rec, partials);
+      CVP_LAUNCH_CHECK();
+      gyration_periodic_finish_kernel<T><<<warp_blocks, 128, 0, st>>>(
+          partials, ns, n, squared, rec, value, accumulate ? 1 : 0, B);
+      CVP_LAUNCH_CHECK();
+    }
+    if (grad == nullptr) return CVP_OK;
+    const bool dense = contiguous && n == N;
+    if (!accumulate && !dense)
+      CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+    gyration_gradient_kernel<T, PBC><<<grid, GYR_THREADS, 0, st>>>(
+        pos, N, idx, w, n, first, ns, box, a.box_mode, rec, grad, accumulate ? 1 : 0);
+    CVP_LAUNCH_CHECK();
+    return CVP_OK;
+  }
+
+  template <typename T>
+  int run_type(const EvalArgs& a, void* ws) {
+    if (!periodic) return run_impl<T, 0>(a, ws);
+    CVP_REQUIRE(a.box != nullptr && a.box_mode != CVP_BOX_NONE,
+                "this collective variable uses periodic boundary conditions but no box was given");
+    return (a.flags & CVP_FLAG_TRICLINIC) ? run_impl<T, 2>(a, ws) : run_impl<T, 1>(a, ws);
+  }
+  int run(const EvalArgs& a, void* ws) override {
+    return a.dtype == CVP_F32 ? run_type<float>(a, ws) : run_type<double>(a, ws);
+  }
+};
+
+}  // namespace
+
+int gyration_create(const cvp_gyration_desc* desc, cvp_cv** out) {
+  CVP_REQUIRE(desc != nullptr && out != nullptr, "null argument");
+  CVP_REQUIRE(desc->num_atoms > 0 && desc->n > 0 && desc->group && desc->weights, "empty group");
+  auto cv = new GyrationCV();
+  cv->num_atoms = desc->num_atoms;
+  cv->group.assign(desc->group, desc->group + desc->n);
+  cv->weights.assign(desc->weights, desc->weights + desc->n);
+  cv->periodic = desc->periodic;
+  cv->squared = desc->squared;
+  std::vector<char> seen(desc->num_atoms, 0);
+  bool contiguous = true;
+  for (int i = 0; i < desc->n; ++i) {
+    int32_t a = cv->group[i];
+    if (a < 0 || a >= desc->num_atoms || seen[a]) {
+      delete cv;
+      set_error(a < 0 || a >= desc->num_atoms ? "atom index out of range in group"
+                                              : "repeated atom in group");
+      return CVP_ERR_INVALID;
+    }
+    seen[a] = 1;
+    if (a != cv->group[0] + i) contiguous = false;
+  }
+  cv->contiguous = contiguous;
+  cv->active_atoms = cv->group;
+  std::sort(cv->active_atoms.begin(), cv->active_atoms.end());
+  *out = cv;
+  return CVP_OK;
+}
+
+}  // namespace cvp

@@ -1,0 +1,521 @@
+// RMSD family, value + gradient, for a batch of frames: RMSD, CompositeRMSD, Helix/SheetRMSDContent
+// and PathInRMSDSpace.
+//
+// Replaces openmm.RMSDForce (cvpack/rmsd.py:96), openmmcppforces.CompositeRMSDForce
+// (composite_rmsd.py:135-137) and the CustomCVForce compositions over RMSD CVs
+// (base_rmsd_content.py:44-79, base_path_cv.py:43-62).
+//
+// A *group* is one optimal-superposition problem.  Its entries (atom, reference row) are sorted by
+// *body*; a (group, body) run is a *segment*, centred on its own centroid in both structures, all
+// segments of a group sharing one rotation (plain RMSD: one segment per group).
+//
+//   R = sum_i x^_i (x) y^_i          (3x3 correlation; y^ pre-centred on the host, so x needs no
+//                                     centring here: sum x^ (x) y^ = sum x (x) y^)
+//   Gx = sum |x|^2 - sum_seg |sum_seg x|^2 / n_seg,  Gy = sum |y^|^2
+//   F(R) Horn's 4x4 matrix, lambda_max, q -> U (rotates x^ onto y^)
+//   msd = max(0, (Gx + Gy - 2 lambda_max)/n);  msd < 1e-20 -> rmsd = 0 with zero gradient
+//   d rmsd/d x_i = (x_i - c_seg(i) - U^T y^_i) / (n rmsd)
+//
+// Stages (one stream, deterministic):
+//   sums      one warp per (frame, slice of <= 1024 entries): 13 double sums
+//   solve     one thread per (frame, group): reduce slices, Jacobi eigen-solve in double
+//   combine   one thread per frame: CV value and d CV / d rmsd_g
+//   gradient  one thread per (frame, active atom): sum over the atom's entries (CSR), single writer
+#include "common.cuh"
+
+namespace cvp {
+namespace {
+
+constexpr int RMSD_SLICE = 1024;
+constexpr int RMSD_WARPS = 8;
+
+struct RmsdSlice {
+  int32_t begin, end;  // entry range
+};
+
+// ---- sums --------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(RMSD_WARPS * 32)
+    rmsd_sums_kernel(const T* __restrict__ pos, int64_t num_atoms,
+                     const int32_t* __restrict__ entry_atom, const double* __restrict__ ref,
+                     const RmsdSlice* __restrict__ slices, int nslice, int64_t num_frames,
+                     double* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (w >= num_frames * nslice) return;
+  const int64_t b = w / nslice;
+  const int s = (int)(w - b * nslice);
+  const RmsdSlice sl = slices[s];
+  const T* frame = pos + b * num_atoms * 3;
+  double v[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) v[k] = 0.0;
+  for (int e = sl.begin + lane; e < sl.end; e += 32) {
+    const int64_t atom = entry_atom[e];
+    const double x = frame[3 * atom], y = frame[3 * atom + 1], z = frame[3 * atom + 2];
+    const double rx = ref[3 * (int64_t)e], ry = ref[3 * (int64_t)e + 1], rz = ref[3 * (int64_t)e + 2];
+    v[0] += x;
+    v[1] += y;
+    v[2] += z;
+    v[3] += x * x + y * y + z * z;
+    v[4] += x * rx;
+    v[5] += x * ry;
+    v[6] += x * rz;
+    v[7] += y * rx;
+    v[8] += y * ry;
+    v[9] += y * rz;
+    v[10] += z * rx;
+    v[11] += z * ry;
+    v[12] += z * rz;
+  }
+#pragma unroll
+  for (int k = 0; k < 13; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 13; ++k) partials[(size_t)w * 13 + k] = v[k];
+  }
+}
+
+// ---- solve -------------------------------------------------------------------------------------
+// Largest eigenpair of a symmetric 4x4 matrix by cyclic Jacobi rotations (double precision; plays
+// the role of the JAMA eigen-decomposition in OpenMM's reference RMSD kernel).
+__device__ inline void jacobi4_max(double (&a)[4][4], double& lambda, double (&q)[4]) {
+  double v[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      diag += a[i][i] * a[i][i];
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) off += a[i][j] * a[i][j];
+    }
+    if (off <= 1e-32 * diag || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+#pragma unroll
+      for (int r = p + 1; r < 4; ++r) {
+        const double apr = a[p][r];
+        if (apr == 0.0) continue;
+        const double theta = (a[r][r] - a[p][p]) / (2.0 * apr);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double akp = a[k][p], akr = a[k][r];
+          a[k][p] = c * akp - s * akr;
+          a[k][r] = s * akp + c * akr;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double apk = a[p][k], ark = a[r][k];
+          a[p][k] = c * apk - s * ark;
+          a[r][k] = s * apk + c * ark;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double vkp = v[k][p], vkr = v[k][r];
+          v[k][p] = c * vkp - s * vkr;
+          v[k][r] = s * vkp + c * vkr;
+        }
+      }
+    }
+  }
+  int best = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (a[i][i] > a[best][best]) best = i;
+  lambda = a[best][best];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = v[k][best];
+}
+
+// Per (frame, group) result.
+struct RmsdSolution {
+  double rmsd;
+  double ut[9];  // U^T, row-major: (U^T y)_c = sum_d ut[3c+d] y_d
+};
+
+__global__ void rmsd_solve_kernel(const double* __restrict__ partials, int nslice,
+                                  const int32_t* __restrict__ group_seg_offsets,
+                                  const int32_t* __restrict__ seg_slice_offsets,
+                                  const int32_t* __restrict__ seg_size,
+                                  const int32_t* __restrict__ group_size,
+                                  const double* __restrict__ group_gy, int num_groups,
+                                  int64_t num_frames, RmsdSolution* __restrict__ solution,
+                                  double* __restrict__ seg_centroid, int nseg) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= num_frames * num_groups) return;
+  const int64_t b = t / num_groups;
+  const int g = (int)(t - b * num_groups);
+  double r[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double gx = 0.0;
+  for (int seg = group_seg_offsets[g]; seg < group_seg_offsets[g + 1]; ++seg) {
+    double sx = 0, sy = 0, sz = 0, s2 = 0;
+    for (int s = seg_slice_offsets[seg]; s < seg_slice_offsets[seg + 1]; ++s) {
+      const double* p = partials + ((size_t)b * nslice + s) * 13;
+      sx += p[0];
+      sy += p[1];
+      sz += p[2];
+      s2 += p[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) r[k] += p[4 + k];
+    }
+    const double inv = 1.0 / seg_size[seg];
+    gx += s2 - (sx * sx + sy * sy + sz * sz) * inv;
+    double* c = seg_centroid + ((size_t)b * nseg + seg) * 3;
+    c[0] = sx * inv;
+    c[1] = sy * inv;
+    c[2] = sz * inv;
+  }
+  const double Sxx = r[0], Sxy = r[1], Sxz = r[2], Syx = r[3], Syy = r[4], Syz = r[5], Szx = r[6],
+               Szy = r[7], Szz = r[8];
+  double f[4][4] = {{Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
+                    {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
+                    {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
+                    {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
+  double lambda, q[4];
+  jacobi4_max(f, lambda, q);
+  const double norm = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double q0 = q[0] * norm, q1 = q[1] * norm, q2 = q[2] * norm, q3 = q[3] * norm;
+  const int n = group_size[g];
+  const double msd = (gx + group_gy[g] - 2.0 * lambda) / n;
+  RmsdSolution sol;
+  sol.rmsd = msd < 1e-20 ? 0.0 : sqrt(msd);
+  // U rotates x^ onto y^; store its transpose
+  const double u00 = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, u01 = 2 * (q1 * q2 - q0 * q3),
+               u02 = 2 * (q1 * q3 + q0 * q2), u10 = 2 * (q1 * q2 + q0 * q3),
+               u11 = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, u12 = 2 * (q2 * q3 - q0 * q1),
+               u20 = 2 * (q1 * q3 - q0 * q2), u21 = 2 * (q2 * q3 + q0 * q1),
+               u22 = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+  sol.ut[0] = u00; sol.ut[1] = u10; sol.ut[2] = u20;
+  sol.ut[3] = u01; sol.ut[4] = u11; sol.ut[5] = u21;
+  sol.ut[6] = u02; sol.ut[7] = u12; sol.ut[8] = u22;
+  solution[t] = sol;
+}
+
+// ---- combine -----------------------------------------------------------------------------------
+struct CombineParams {
+  int mode;
+  StepParams step;
+  double inv_r0, scale, lambda;  // lambda = 1/(2 sigma^2)
+};
+
+// One thread per frame.  Writes the CV value and, per group, the factor multiplying
+// (x_i - c - U^T y_i) in the gradient: dCV/drmsd_g / (n_g rmsd_g)  (0 for a degenerate group).
+template <typename T>
+__global__ void rmsd_combine_kernel(const RmsdSolution* __restrict__ solution,
+                                    const int32_t* __restrict__ group_size, int num_groups,
+                                    CombineParams cp, T* __restrict__ value,
+                                    double* __restrict__ group_factor, int accumulate,
+                                    int64_t num_frames) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= num_frames) return;
+  const RmsdSolution* sol = solution + b * num_groups;
+  double* factor = group_factor + b * num_groups;
+  double result = 0.0;
+  if (cp.mode == CVP_COMBINE_IDENTITY) {
+    result = sol[0].rmsd;
+    factor[0] = result > 0.0 ? 1.0 / (group_size[0] * result) : 0.0;
+  } else if (cp.mode == CVP_COMBINE_STEP_SUM) {
+    for (int g = 0; g < num_groups; ++g) {
+      const double d = sol[g].rmsd;
+      double s, ds;
+      step_function(cp.step, d * cp.inv_r0, s, ds);
+      result += s;
+      factor[g] = d > 0.0 ? cp.scale * ds * cp.inv_r0 / (group_size[g] * d) : 0.0;
+    }
+    result *= cp.scale;
+  } else {
+    // x_g = rmsd_g^2, w_g = exp(lambda (xmin - x_g))  (base_path_cv.py:44-59)
+    double xmin = sol[0].rmsd * sol[0].rmsd;
+    for (int g = 1; g < num_groups; ++g) xmin = fmin(xmin, sol[g].rmsd * sol[g].rmsd);
+    double wsum = 0.0, iwsum = 0.0;
+    for (int g = 0; g < num_groups; ++g) {
+      const double w = exp(cp.lambda * (xmin - sol[g].rmsd * sol[g].rmsd));
+      wsum += w;
+      iwsum += g * w;
+    }
+    const double s = iwsum / ((num_groups - 1) * wsum);
+    result = cp.mode == CVP_COMBINE_PATH_PROGRESS ? s : xmin - log(wsum) / cp.lambda;
+    for (int g = 0; g < num_groups; ++g) {
+      const double w = exp(cp.lambda * (xmin - sol[g].rmsd * sol[g].rmsd));
+      // dCV/dx_g, then dx_g/drmsd_g = 2 rmsd_g, then 1/(n_g rmsd_g)
+      const double dx = cp.mode == CVP_COMBINE_PATH_PROGRESS
+                            ? -cp.lambda * w * ((double)g / (num_groups - 1) - s) / wsum
+                            : w / wsum;
+      factor[g] = sol[g].rmsd > 0.0 ? 2.0 * dx / group_size[g] : 0.0;
+    }
+  }
+  value[b] = accumulate ? T((double)value[b] + result) : T(result);
+}
+
+// ---- gradient ----------------------------------------------------------------------------------
+template <typename T>
+__global__ void rmsd_gradient_kernel(const T* __restrict__ pos, int64_t num_atoms,
+                                     const int32_t* __restrict__ active_atom,
+                                     const int32_t* __restrict__ atom_entry_offsets,
+                                     const int32_t* __restrict__ atom_entries, int num_active,
+                                     const int32_t* __restrict__ entry_group,
+                                     const int32_t* __restrict__ entry_seg,
+                                     const double* __restrict__ ref,
+                                     const RmsdSolution* __restrict__ solution,
+                                     const double* __restrict__ seg_centroid,
+                                     const double* __restrict__ group_factor, int num_groups,
+                                     int nseg, T* __restrict__ grad, int accumulate,
+                                     int64_t total) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int64_t b = t / num_active;
+  const int k = (int)(t - b * num_active);
+  const int64_t atom = active_atom[k];
+  const T* p = pos + (b * num_atoms + atom) * 3;
+  const double x = p[0], y = p[1], z = p[2];
+  double gx = 0, gy = 0, gz = 0;
+  for (int m = atom_entry_offsets[k]; m < atom_entry_offsets[k + 1]; ++m) {
+    const int e = atom_entries[m];
+    const int g = entry_group[e];
+    const double f = group_factor[b * num_groups + g];
+    if (f == 0.0) continue;
+    const double* c = seg_centroid + ((size_t)b * nseg + entry_seg[e]) * 3;
+    const double* ut = solution[b * num_groups + g].ut;
+    const double rx = ref[3 * (int64_t)e], ry = ref[3 * (int64_t)e + 1], rz = ref[3 * (int64_t)e + 2];
+    gx += f * (x - c[0] - (ut[0] * rx + ut[1] * ry + ut[2] * rz));
+    gy += f * (y - c[1] - (ut[3] * rx + ut[4] * ry + ut[5] * rz));
+    gz += f * (z - c[2] - (ut[6] * rx + ut[7] * ry + ut[8] * rz));
+  }
+  T* out = grad + (b * num_atoms + atom) * 3;
+  if (accumulate) {
+    out[0] += T(gx);
+    out[1] += T(gy);
+    out[2] += T(gz);
+  } else {
+    out[0] = T(gx);
+    out[1] = T(gy);
+    out[2] = T(gz);
+  }
+}
+
+struct RmsdCV : cvp_cv {
+  int num_groups = 0, nseg = 0, nslice = 0;
+  int64_t num_entries = 0;
+  CombineParams cp{};
+  std::vector<int32_t> entry_atom, entry_group, entry_seg;
+  std::vector<double> ref;  // centred per segment
+  std::vector<RmsdSlice> slices;
+  std::vector<int32_t> group_seg_offsets, seg_slice_offsets, seg_size, group_size;
+  std::vector<double> group_gy;
+  std::vector<int32_t> atom_entry_offsets, atom_entries;
+  bool dense = false;  // every atom of the system is active
+  DeviceBuffer d_entry_atom, d_entry_group, d_entry_seg, d_ref, d_slices, d_group_seg_offsets,
+      d_seg_slice_offsets, d_seg_size, d_group_size, d_group_gy, d_active, d_atom_entry_offsets,
+      d_atom_entries;
+
+  ~RmsdCV() override {
+    for (DeviceBuffer* buf :
+         {&d_entry_atom, &d_entry_group, &d_entry_seg, &d_ref, &d_slices, &d_group_seg_offsets,
+          &d_seg_slice_offsets, &d_seg_size, &d_group_size, &d_group_gy, &d_active,
+          &d_atom_entry_offsets, &d_atom_entries})
+      buf->release();
+  }
+  int upload() override {
+    int status;
+#define CVP_UP(buf, vec) \
+  if ((status = cvp::upload(buf, vec)) != CVP_OK) return status
+    CVP_UP(d_entry_atom, entry_atom);
+    CVP_UP(d_entry_group, entry_group);
+    CVP_UP(d_entry_seg, entry_seg);
+    CVP_UP(d_ref, ref);
+    CVP_UP(d_slices, slices);
+    CVP_UP(d_group_seg_offsets, group_seg_offsets);
+    CVP_UP(d_seg_slice_offsets, seg_slice_offsets);
+    CVP_UP(d_seg_size, seg_size);
+    CVP_UP(d_group_size, group_size);
+    CVP_UP(d_group_gy, group_gy);
+    CVP_UP(d_active, active_atoms);
+    CVP_UP(d_atom_entry_offsets, atom_entry_offsets);
+    CVP_UP(d_atom_entries, atom_entries);
+#undef CVP_UP
+    return CVP_OK;
+  }
+  size_t workspace_per_frame(int, bool) const override {
+    return (size_t)nslice * 13 * sizeof(double) + (size_t)num_groups * sizeof(RmsdSolution) +
+           (size_t)nseg * 3 * sizeof(double) + (size_t)num_groups * sizeof(double) + 64;
+  }
+  size_t workspace_fixed(int) const override { return 6 * 256; }
+  int64_t max_frames_per_run() const override {
+    int64_t per_frame = std::max<int64_t>(nslice, (int64_t)active_atoms.size() / 64 + 1);
+    return std::max<int64_t>(1, (int64_t(1) << 30) / per_frame);
+  }
+
+  template <typename T>
+  int run_type(const EvalArgs& a, void* ws) {
+    const int64_t B = a.num_frames, N = a.num_atoms;
+    const bool accumulate = (a.flags & CVP_FLAG_ACCUMULATE) != 0;
+    const T* pos = static_cast<const T*>(a.positions);
+    T* value = static_cast<T*>(a.value);
+    T* grad = static_cast<T*>(a.grad);
+    cudaStream_t st = a.stream;
+    Carver carve(ws);
+    double* partials = carve.take<double>((size_t)B * nslice * 13);
+    RmsdSolution* solution = carve.take<RmsdSolution>((size_t)B * num_groups);
+    double* seg_centroid = carve.take<double>((size_t)B * nseg * 3);
+    double* group_factor = carve.take<double>((size_t)B * num_groups);
+
+    {
+      int64_t warps = B * nslice;
+      rmsd_sums_kernel<T><<<(unsigned)div_up(warps, RMSD_WARPS), RMSD_WARPS * 32, 0, st>>>(
+          pos, N, static_cast<const int32_t*>(d_entry_atom.ptr),
+          static_cast<const double*>(d_ref.ptr), static_cast<const RmsdSlice*>(d_slices.ptr),
+          nslice, B, partials);
+      CVP_LAUNCH_CHECK();
+    }
+    {
+      int64_t total = B * num_groups;
+      rmsd_solve_kernel<<<(unsigned)div_up(total, 64), 64, 0, st>>>(
+          partials, nslice, static_cast<const int32_t*>(d_group_seg_offsets.ptr),
+          static_cast<const int32_t*>(d_seg_slice_offsets.ptr),
+          static_cast<const int32_t*>(d_seg_size.ptr),
+          static_cast<const int32_t*>(d_group_size.ptr),
+          static_cast<const double*>(d_group_gy.ptr), num_groups, B, solution, seg_centroid, nseg);
+      CVP_LAUNCH_CHECK();
+    }
+    rmsd_combine_kernel<T><<<(unsigned)div_up(B, 128), 128, 0, st>>>(
+        solution, static_cast<const int32_t*>(d_group_size.ptr), num_groups, cp, value,
+        group_factor, accumulate ? 1 : 0, B);
+    CVP_LAUNCH_CHECK();
+    if (grad == nullptr) return CVP_OK;
+    if (!accumulate && !dense)
+      CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+    {
+      const int num_active = (int)active_atoms.size();
+      int64_t total = B * (int64_t)num_active;
+      rmsd_gradient_kernel<T><<<(unsigned)div_up(total, 256), 256, 0, st>>>(
+          pos, N, static_cast<const int32_t*>(d_active.ptr),
+          static_cast<const int32_t*>(d_atom_entry_offsets.ptr),
+          static_cast<const int32_t*>(d_atom_entries.ptr), num_active,
+          static_cast<const int32_t*>(d_entry_group.ptr),
+          static_cast<const int32_t*>(d_entry_seg.ptr), static_cast<const double*>(d_ref.ptr),
+          solution, seg_centroid, group_factor, num_groups, nseg, grad, accumulate ? 1 : 0, total);
+      CVP_LAUNCH_CHECK();
+    }
+    return CVP_OK;
+  }
+  int run(const EvalArgs& a, void* ws) override {
+    return a.dtype == CVP_F32 ? run_type<float>(a, ws) : run_type<double>(a, ws);
+  }
+};
+
+}  // namespace
+
+int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
+  CVP_REQUIRE(desc != nullptr && out != nullptr, "null argument");
+  CVP_REQUIRE(desc->num_atoms > 0 && desc->num_groups > 0 && desc->group_offsets && desc->atoms &&
+                  desc->reference,
+              "empty RMSD description");
+  CVP_REQUIRE(desc->combine >= CVP_COMBINE_IDENTITY && desc->combine <= CVP_COMBINE_PATH_DEVIATION,
+              "unknown combine rule");
+  CVP_REQUIRE(desc->combine != CVP_COMBINE_IDENTITY || desc->num_groups == 1,
+              "identity combine needs exactly one group");
+  if (desc->combine >= CVP_COMBINE_PATH_PROGRESS)
+    CVP_REQUIRE(desc->num_groups >= 2 && desc->sigma > 0, "path needs >= 2 groups and sigma > 0");
+  if (desc->combine == CVP_COMBINE_STEP_SUM)
+    CVP_REQUIRE(desc->r0 > 0 && desc->step_kind >= CVP_STEP_RATIONAL &&
+                    desc->step_kind <= CVP_STEP_PLUMED,
+                "bad step function");
+  const int G = desc->num_groups;
+  const int64_t E = desc->group_offsets[G];
+  CVP_REQUIRE(desc->group_offsets[0] == 0 && E > 0 && E < (int64_t(1) << 31), "bad group offsets");
+
+  auto cv = new RmsdCV();
+  cv->num_atoms = desc->num_atoms;
+  cv->num_groups = G;
+  cv->num_entries = E;
+  cv->cp.mode = desc->combine;
+  cv->cp.step.kind = desc->step_kind;
+  cv->cp.step.n = (int)desc->step_p0;
+  cv->cp.step.m = (int)desc->step_p1;
+  cv->cp.inv_r0 = desc->r0 > 0 ? 1.0 / desc->r0 : 1.0;
+  cv->cp.scale = desc->scale;
+  cv->cp.lambda = desc->sigma > 0 ? 1.0 / (2.0 * desc->sigma * desc->sigma) : 0.0;
+
+  auto fail = [&](const char* message) {
+    delete cv;
+    set_error(message);
+    return CVP_ERR_INVALID;
+  };
+  cv->group_seg_offsets.push_back(0);
+  cv->seg_slice_offsets.push_back(0);
+  std::vector<char> seen(desc->num_atoms, 0);
+  for (int g = 0; g < G; ++g) {
+    const int begin = desc->group_offsets[g], end = desc->group_offsets[g + 1];
+    if (end <= begin) return fail("empty RMSD group");
+    // stable order of entries by body id
+    std::vector<int32_t> order(end - begin);
+    for (int k = 0; k < end - begin; ++k) order[k] = begin + k;
+    if (desc->body_ids)
+      std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return desc->body_ids[x] < desc->body_ids[y];
+      });
+    std::fill(seen.begin(), seen.end(), 0);
+    double gy = 0.0;
+    size_t k = 0;
+    while (k < order.size()) {
+      const int body = desc->body_ids ? desc->body_ids[order[k]] : 0;
+      size_t k2 = k;
+      double c[3] = {0, 0, 0};
+      while (k2 < order.size() && (desc->body_ids ? desc->body_ids[order[k2]] : 0) == body) {
+        for (int d = 0; d < 3; ++d) c[d] += desc->reference[3 * (size_t)order[k2] + d];
+        ++k2;
+      }
+      const int count = (int)(k2 - k);
+      for (int d = 0; d < 3; ++d) c[d] /= count;
+      const int seg = (int)cv->seg_size.size();
+      const int seg_begin = (int)cv->entry_atom.size();
+      for (size_t m = k; m < k2; ++m) {
+        const int32_t atom = desc->atoms[order[m]];
+        if (atom < 0 || atom >= desc->num_atoms) return fail("atom index out of range in RMSD group");
+        if (seen[atom]) return fail("repeated atom in RMSD group");
+        seen[atom] = 1;
+        cv->entry_atom.push_back(atom);
+        cv->entry_group.push_back(g);
+        cv->entry_seg.push_back(seg);
+        for (int d = 0; d < 3; ++d) {
+          const double y = desc->reference[3 * (size_t)order[m] + d] - c[d];
+          cv->ref.push_back(y);
+          gy += y * y;
+        }
+      }
+      cv->seg_size.push_back(count);
+      for (int s = seg_begin; s < seg_begin + count; s += RMSD_SLICE)
+        cv->slices.push_back({s, std::min(s + RMSD_SLICE, seg_begin + count)});
+      cv->seg_slice_offsets.push_back((int32_t)cv->slices.size());
+      k = k2;
+    }
+    cv->group_seg_offsets.push_back((int32_t)cv->seg_size.size());
+    cv->group_size.push_back(end - begin);
+    cv->group_gy.push_back(gy);
+  }
+  cv->nseg = (int)cv->seg_size.size();
+  cv->nslice = (int)cv->slices.size();
+  // atom -> entries (CSR over sorted active atoms)
+  {
+    std::vector<std::vector<int32_t>> by_atom(desc->num_atoms);
+    for (int64_t e = 0; e < E; ++e) by_atom[cv->entry_atom[e]].push_back((int32_t)e);
+    cv->atom_entry_offsets.push_back(0);
+    for (int a = 0; a < desc->num_atoms; ++a) {
+      if (by_atom[a].empty()) continue;
+      cv->active_atoms.push_back(a);
+      for (int32_t e : by_atom[a]) cv->atom_entries.push_back(e);
+      cv->atom_entry_offsets.push_back((int32_t)cv->atom_entries.size());
+    }
+    cv->dense = (int)cv->active_atoms.size() == desc->num_atoms;
+  }
+  *out = cv;
+  return CVP_OK;
+}
+
+}  // namespace cvp

@@ -1,0 +1,230 @@
+/*
+ * cvpack_b200 -- C ABI of the B200-native batched collective-variable evaluator.
+ *
+ * The reference (RedesignScience/cvpack) has no FFI of its own: each CV is an OpenMM Force and the
+ * boundary under its Python API is `openmm.Context.getState(getEnergy|getForces, groups=1<<g)`
+ * (cvpack/utils.py:140) -- "energy" is the CV value, "forces" are minus its gradient, one frame per
+ * call.  This header is what a binding for that path would bind instead: a CV is compiled once
+ * into an opaque kernel spec (`cvp_cv`, the analogue of the OpenMM Force object the cvpack
+ * constructor configures) and then evaluated for a whole batch of frames per call.
+ *
+ * Conventions
+ *   - coordinates: nm, row-major [B][N][3], float (CVP_F32) or double (CVP_F64)
+ *   - gradient: +dCV/dr, same layout and type as the coordinates (OpenMM forces = -gradient)
+ *   - box: three row vectors a,b,c as 9 numbers (same type as coordinates); CVP_BOX_SHARED = one
+ *     box [9] for every frame, CVP_BOX_PER_FRAME = [B][9].  Must be in OpenMM's reduced form
+ *     (a=(ax,0,0), b=(bx,by,0), c=(cx,cy,cz)).  Set CVP_FLAG_TRICLINIC if any off-diagonal != 0.
+ *   - atom indices: int32, 0-based, < num_atoms; index handling is exact (no float round trips)
+ *   - every function returns CVP_OK (0) or a negative cvp_status; nothing throws across the ABI;
+ *     cvp_last_error() gives the message of the last failure on the calling thread
+ *   - the caller owns every buffer; the library owns only spec-internal device copies of index /
+ *     parameter arrays and a per-spec workspace, both released by cvp_destroy
+ *   - cvp_evaluate is asynchronous with respect to the host and ordered on `stream`; a spec must not
+ *     be evaluated concurrently from two streams (its workspace is shared)
+ */
+#ifndef CVPACK_B200_H
+#define CVPACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cvp_cv cvp_cv;
+
+typedef enum {
+  CVP_OK = 0,
+  CVP_ERR_INVALID = -1,     /* bad argument (null pointer, index out of range, size mismatch)   */
+  CVP_ERR_CUDA = -2,        /* a CUDA runtime call failed; message has the CUDA error string      */
+  CVP_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve                              */
+  CVP_ERR_NO_DEVICE = -4    /* no usable sm_100 device                                            */
+} cvp_status;
+
+enum { CVP_F32 = 0, CVP_F64 = 1 };
+enum { CVP_BOX_NONE = 0, CVP_BOX_SHARED = 1, CVP_BOX_PER_FRAME = 2 };
+enum {
+  CVP_FLAG_TRICLINIC = 1,   /* box has non-zero off-diagonal elements                             */
+  CVP_FLAG_ACCUMULATE = 2   /* add into value/grad instead of overwriting them                    */
+};
+
+/* Step functions S(x) used by contact-type sums (the whitelisted forms of cvpack's `stepFunction`
+ * strings; number_of_contacts.py:132, residue_coordination.py:113, helix_rmsd_content.py:135). */
+enum {
+  CVP_STEP_RATIONAL = 0,    /* 1/(1+x^n), n = p0 (any positive integer)                           */
+  CVP_STEP_HEAVISIDE = 1,   /* step(1-x): 1 if x <= 1 else 0; zero gradient                       */
+  CVP_STEP_RATIONAL_PAIR = 2, /* (1+x^n)/(1+x^n+x^(2n)), n = p0                                   */
+  CVP_STEP_PLUMED = 3       /* (1-x^n)/(1-x^m), n = p0, m = p1; n/m at x == 1                      */
+};
+
+/* ---- pair sums: NumberOfContacts, AttractionStrength, ShortestDistance ---------------------- */
+/* Replaces an OpenMM CustomNonbondedForce with one interaction group (group1, group2):
+ * number_of_contacts.py:143-161, attraction_strength.py:189-231, shortest_distance.py:122-138.
+ * The sum runs over unordered pairs {i,j}, i in group1, j in group2, i != j, each pair once even
+ * if both atoms are in both groups, excluding `exclusions`, and only r < cutoff.                 */
+enum {
+  CVP_PAIR_CONTACTS = 0,    /* scale * sum S(r/r0) * sw(r)                                        */
+  CVP_PAIR_ATTRACTION = 1,  /* scale * sum -sgn_i sgn_j [4 eps (1/y^2-1/y) + ke min(0,qiqj)(1/x+(x^2-3)/2)] sw(r) */
+  CVP_PAIR_SOFTMIN = 2      /* (rc e^-beta + sum r w)/(e^-beta + sum w), w = exp(-beta r/rc)       */
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t num_atoms;
+  int32_t n1;
+  const int32_t* group1;
+  int32_t n2;
+  const int32_t* group2;
+  int32_t num_exclusions;
+  const int32_t* exclusions;   /* [num_exclusions][2] atom pairs never counted                    */
+  int32_t periodic;            /* minimum-image convention on/off                                 */
+  double cutoff;               /* r >= cutoff skipped; <= 0 means no cutoff                       */
+  double switch_distance;      /* sw(r) = 1 - 10t^3 + 15t^4 - 6t^5 for r > it; <= 0 means none    */
+  double scale;                /* 1/reference                                                     */
+  int32_t step_kind;           /* CVP_PAIR_CONTACTS                                               */
+  double step_p0, step_p1;
+  double r0;                   /* threshold distance of the step function                         */
+  const double* charge;        /* CVP_PAIR_ATTRACTION: per atom [num_atoms]                       */
+  const double* sigma;
+  const double* epsilon;
+  const double* sign;          /* may be NULL (all +1)                                            */
+  double coulomb_constant;     /* 138.93545764438198 kJ nm /(mol e^2)                             */
+  double beta;                 /* CVP_PAIR_SOFTMIN                                                */
+} cvp_pair_sum_desc;
+
+int cvp_pair_sum_create(const cvp_pair_sum_desc* desc, cvp_cv** out);
+
+/* ---- centroid pair sums: ResidueCoordination -------------------------------------------------- */
+/* Replaces CustomCentroidBondForce(2, ...) with one bond per (residue of set 1, residue of set 2):
+ * residue_coordination.py:129-144.  value = scale * sum_{I<n1} sum_{J<n2} S(|R_J - R_I|/r0),
+ * R = sum_a w_a r_a over raw coordinates, minimum image on R_J - R_I only.                        */
+typedef struct {
+  int32_t num_atoms;
+  int32_t n1, n2;                 /* number of centroid groups in each set                        */
+  const int32_t* group_offsets;   /* [n1+n2+1] CSR offsets into group_atoms / group_weights        */
+  const int32_t* group_atoms;
+  const double* group_weights;    /* normalised within each group                                 */
+  int32_t periodic;
+  int32_t step_kind;
+  double step_p0, step_p1;
+  double r0;
+  double scale;
+} cvp_centroid_pair_sum_desc;
+
+int cvp_centroid_pair_sum_create(const cvp_centroid_pair_sum_desc* desc, cvp_cv** out);
+
+/* ---- RMSD family: RMSD, CompositeRMSD, Helix/SheetRMSDContent, PathInRMSDSpace ---------------- */
+/* Replaces openmm.RMSDForce (rmsd.py:96), openmmcppforces.CompositeRMSDForce (composite_rmsd.py:
+ * 135-137) and the CustomCVForce compositions over RMSD CVs (base_rmsd_content.py:44-79,
+ * base_path_cv.py:43-62).  Each *group* is one optimal-superposition problem; each group may be
+ * split in *bodies* centred separately but rotated together (composite RMSD).                     */
+enum {
+  CVP_COMBINE_IDENTITY = 0,       /* value = rmsd of the single group                             */
+  CVP_COMBINE_STEP_SUM = 1,       /* value = scale * sum_g S(rmsd_g/r0)                           */
+  CVP_COMBINE_PATH_PROGRESS = 2,  /* s = sum_g g w_g /((G-1) sum w),  w_g = exp(-rmsd_g^2/(2 sigma^2)) */
+  CVP_COMBINE_PATH_DEVIATION = 3  /* z = -2 sigma^2 ln sum_g w_g                                  */
+};
+
+typedef struct {
+  int32_t num_atoms;
+  int32_t num_groups;
+  const int32_t* group_offsets;   /* [num_groups+1] CSR offsets into atoms / body_ids / reference  */
+  const int32_t* atoms;           /* atom index of each entry; order pairs with reference rows     */
+  const int32_t* body_ids;        /* body of each entry within its group, 0-based; NULL = all 0    */
+  const double* reference;        /* [entries][3] reference coordinates (any origin)               */
+  int32_t combine;
+  int32_t step_kind;
+  double step_p0, step_p1;
+  double r0;
+  double scale;
+  double sigma;
+} cvp_rmsd_desc;
+
+int cvp_rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out);
+
+/* ---- radius of gyration: RadiusOfGyration, RadiusOfGyrationSq --------------------------------- */
+/* Replaces the CustomCentroidBondForce constructions of radius_of_gyration.py:85-92 and
+ * radius_of_gyration_sq.py:87-89: rg^2 = (1/n) sum_i |r_i - c|^2, c = sum_i w_i r_i.            */
+typedef struct {
+  int32_t num_atoms;
+  int32_t n;
+  const int32_t* group;
+  const double* weights;          /* [n] weights of the centre, normalised (1/n or m_i/M)          */
+  int32_t periodic;               /* minimum image on each r_i - c                                 */
+  int32_t squared;                /* 1: value = rg^2 (nm^2); 0: value = rg (nm)                     */
+} cvp_gyration_desc;
+
+int cvp_gyration_create(const cvp_gyration_desc* desc, cvp_cv** out);
+
+/* ---- bonded terms: Distance, Angle, Torsion, Helix{Torsion,Angle,HBond}Content ---------------- */
+/* Replaces CustomBondForce / CustomAngleForce / CustomTorsionForce with one expression for all
+ * terms (distance.py:57-59, angle.py:73-75, torsion.py:80-82, helix_torsion_content.py:126-145,
+ * helix_angle_content.py:118-128, helix_hbond_content.py:104-114).
+ * value = sum_t f(q_t): q = |r2-r1| (2 atoms), acos angle at atom 2 (3 atoms), or the dihedral
+ * (4 atoms, sign convention of torsion.py:22-33).                                                 */
+enum {
+  CVP_TERM_IDENTITY = 0,          /* f(q) = coefficient * q                                        */
+  CVP_TERM_BOXCAR = 1             /* f(q) = coefficient / (1 + x^(2m)), x = (q - ref_t)/tolerance   */
+};
+
+typedef struct {
+  int32_t num_atoms;
+  int32_t num_terms;
+  int32_t atoms_per_term;         /* 2, 3 or 4                                                     */
+  const int32_t* atoms;           /* [num_terms][atoms_per_term]                                   */
+  int32_t function;
+  const double* reference;        /* [num_terms] (CVP_TERM_BOXCAR), may be NULL otherwise          */
+  double tolerance;
+  int32_t half_exponent;          /* m                                                             */
+  double coefficient;
+  int32_t periodic;
+} cvp_bonded_desc;
+
+int cvp_bonded_create(const cvp_bonded_desc* desc, cvp_cv** out);
+
+/* ---- lifetime, evaluation ---------------------------------------------------------------------- */
+int cvp_destroy(cvp_cv* cv);
+
+/* Number of atoms that can carry a non-zero gradient, and their sorted indices (for compact
+ * gathers across GPUs).  `atoms` may be NULL to query the count only.                             */
+int cvp_active_atoms(const cvp_cv* cv, int32_t* count, int32_t* atoms);
+
+/* Evaluate on DEVICE buffers, asynchronously on `stream` (a cudaStream_t; NULL = default stream).
+ * `value` [B] and `grad` [B][N][3] have the coordinate type; `grad` may be NULL (value only).
+ * Replaces Context.getState(getEnergy=True, getForces=True, groups=1<<g) per frame
+ * (cvpack/utils.py:140).                                                                          */
+int cvp_evaluate(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
+                 int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,
+                 void* stream);
+
+/* Same through HOST buffers (pinned for full speed): frames are cut in chunks that flow through
+ * host->device copy, kernels and device->host copy on separate streams.  Synchronous.            */
+int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
+                      int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,
+                      int device);
+
+/* Effective mass 1/sum_i |g_i|^2/m_i over atoms with non-zero gradient, +inf if none
+ * (cvpack/utils.py:172-184).  `grad` [B][N][3] device, `masses` [N] device double, `emass` [B]
+ * device, coordinate type.                                                                        */
+int cvp_effective_mass(int dtype, const void* grad, const double* masses, int64_t num_frames,
+                       int64_t num_atoms, void* emass, void* stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------- */
+const char* cvp_last_error(void);
+int cvp_version(void);
+/* SM count and compute capability of a device; CVP_ERR_NO_DEVICE if there is none.               */
+int cvp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+/* Kernels launched by this library since the process started (all threads).                     */
+int64_t cvp_launch_count(void);
+/* Bytes of per-spec device workspace a spec may use per evaluate call (default 1 GiB).           */
+int cvp_set_workspace_limit(cvp_cv* cv, int64_t bytes);
+/* Per-family tuning switch (meaning documented in DESIGN.md); returns previous value.            */
+int cvp_set_option(cvp_cv* cv, const char* name, int value);
+/* Sustained FP32 FMA throughput of `device` in TFLOP/s measured by a register-resident FFMA loop
+ * (the FP32 roofline denominator of the pair kernels).                                           */
+int cvp_measure_fp32_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVPACK_B200_H */
