@@ -1,0 +1,384 @@
+"""
+GPU parity: every collective variable, evaluated by the CUDA library through the public Python API
+(ctypes -> C ABI), against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-5 relative in FP32 mode, 1e-10 in FP64 mode.  Values are
+compared relative to |value|; gradients relative to the largest gradient component of the frame
+(per-element relative error is meaningless for components that cancel to ~0).  The oracle sees the
+coordinates after rounding to the GPU's storage precision.
+"""
+
+import io
+
+import numpy as np
+import pytest
+
+import cvpack_b200 as cvpack
+from cvpack_b200 import mmunit, serialization
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"single": (1e-5, 1e-5), "double": (1e-10, 1e-10)}
+ORTHO = np.diag([2.4, 2.6, 2.8])
+TRICLINIC = np.array([[2.4, 0, 0], [0.3, 2.6, 0], [-0.4, 0.5, 2.8]])
+BOXES = {"none": None, "ortho": ORTHO, "triclinic": TRICLINIC}
+
+
+def frames(rng, num_frames, num_atoms, scale=2.4):
+    return rng.uniform(0.0, scale, size=(num_frames, num_atoms, 3))
+
+
+def run(cv, system, positions, box, precision):
+    vt, gt = TOL[precision]
+    return helpers.check_against_oracle(cv, system, positions, box, precision, vt, gt)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("boxname", ["none", "ortho", "triclinic"])
+def test_bonded(precision, boxname):
+    rng = np.random.default_rng(11)
+    box = BOXES[boxname]
+    system = helpers.make_system(40, rng)
+    x = frames(rng, 5, 40)
+    pbc = box is not None
+    run(cvpack.Distance(3, 17, pbc=pbc), system, x, box, precision)
+    run(cvpack.Angle(3, 17, 5, pbc=pbc), system, x, box, precision)
+    run(cvpack.Torsion(3, 17, 5, 9, pbc=pbc), system, x, box, precision)
+
+
+def test_known_answers():
+    """distance.py:37-50, angle.py:46-60, torsion.py:53-67 of the reference."""
+    system = cvpack.System()
+    for _ in range(4):
+        system.addParticle(1.0)
+    distance = cvpack.Distance(0, 1)
+    angle = cvpack.Angle(0, 1, 2)
+    torsion = cvpack.Torsion(0, 1, 2, 3)
+    for cv in (distance, angle, torsion):
+        cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, [[0, 0, 0], [1, 1, 1], [0, 0, 0], [0, 0, 0]], precision="double")
+    assert float(distance.getValue(ctx).value_in_unit(mmunit.nanometers)[0]) == pytest.approx(np.sqrt(3))
+    ctx.setPositions([[0, 0, 0], [0, 0, 1], [0, 1, 1], [0, 0, 0]])
+    assert float(angle.getValue(ctx).value_in_unit(mmunit.radians)[0]) == pytest.approx(np.pi / 2)
+    ctx.setPositions([[0, 0, 0], [1, 0, 0], [1, 1, 0], [1, 1, 1]])
+    assert float(torsion.getValue(ctx).value_in_unit(mmunit.radians)[0]) == pytest.approx(np.pi / 2)
+    assert str(distance.getValue(ctx).unit.get_symbol()) == "nm"
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("boxname", ["none", "ortho", "triclinic"])
+@pytest.mark.parametrize("weigh", [False, True])
+def test_radius_of_gyration(precision, boxname, weigh):
+    rng = np.random.default_rng(12)
+    box = BOXES[boxname]
+    system = helpers.make_system(300, rng)
+    x = frames(rng, 4, 300, scale=1.0) + 5.0  # far from the origin: exercises the cancellation
+    pbc = box is not None
+    group = rng.permutation(300)[:120]
+    run(cvpack.RadiusOfGyration(group, pbc=pbc, weighByMass=weigh), system, x, box, precision)
+    run(cvpack.RadiusOfGyrationSq(range(300), pbc=pbc, weighByMass=weigh), system, x, box, precision)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("boxname", ["none", "ortho", "triclinic"])
+@pytest.mark.parametrize("case", ["disjoint", "overlap", "same", "noswitch", "heaviside"])
+def test_number_of_contacts(precision, boxname, case):
+    rng = np.random.default_rng(13)
+    box = BOXES[boxname]
+    n = 700
+    system = helpers.make_system(n, rng)
+    x = frames(rng, 3, n)
+    nb = helpers.make_nonbonded(n, rng, periodic=box is not None, num_exceptions=60)
+    if case == "disjoint":
+        g1, g2 = range(0, 300), range(300, 700)
+    elif case == "overlap":
+        g1, g2 = range(0, 400), range(250, 700)
+    elif case == "same":
+        g1 = g2 = range(100, 420)
+    else:
+        g1, g2 = rng.permutation(n)[:333], rng.permutation(n)[:290]
+    kwargs = {}
+    if case == "noswitch":
+        kwargs["switchFactor"] = None
+    if case == "heaviside":
+        kwargs["stepFunction"] = "step(1-x)"
+    cv = cvpack.NumberOfContacts(g1, g2, nb, thresholdDistance=0.3 * mmunit.nanometers, **kwargs)
+    vt, gt = TOL[precision]
+    if case in ("noswitch", "heaviside"):
+        # a sharp cutoff makes the value discontinuous: pairs within rounding of r_c may flip
+        vt = max(vt, 5e-4)
+    helpers.check_against_oracle(cv, system, x, box, precision, vt, gt)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_number_of_contacts_reference_context(precision):
+    rng = np.random.default_rng(14)
+    n = 200
+    system = helpers.make_system(n, rng)
+    x = frames(rng, 2, n, scale=1.2)
+    nb = helpers.make_nonbonded(n, rng, periodic=False)
+    plain = cvpack.NumberOfContacts(range(0, 100), range(100, 200), nb)
+    plain.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, precision=precision)
+    raw = plain.getValue(ctx)
+    normalized = cvpack.NumberOfContacts(range(0, 100), range(100, 200), nb, reference=ctx)
+    normalized.addToSystem(system)
+    ctx.reinitialize(preserveState=True)
+    value = normalized.getValue(ctx)
+    assert float(value._value[0]) == pytest.approx(1.0, rel=1e-5)
+    assert float(value._value[1]) == pytest.approx(float(raw._value[1] / raw._value[0]), rel=1e-5)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("boxname", ["none", "ortho"])
+@pytest.mark.parametrize("contrast", [False, True])
+def test_attraction_strength(precision, boxname, contrast):
+    rng = np.random.default_rng(15)
+    box = BOXES[boxname]
+    n = 400
+    system = helpers.make_system(n, rng)
+    # keep atoms apart (a lattice with jitter): the soft-core LJ is stiff at tiny separations
+    grid = np.stack(np.meshgrid(*[np.arange(8)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n] * 0.3
+    x = grid[None] + rng.normal(scale=0.03, size=(3, n, 3))
+    nb = helpers.make_nonbonded(n, rng, periodic=box is not None, cutoff=0.9, switch=0.7, num_exceptions=40)
+    cv = cvpack.AttractionStrength(
+        range(0, 120), range(120, 260), nb,
+        contrastGroup=range(200, 400) if contrast else None, contrastScaling=0.5,
+        reference=25.0 * mmunit.kilojoule_per_mole,
+    )
+    vt, gt = TOL[precision]
+    helpers.check_against_oracle(cv, system, x, box, precision, 4 * vt, 4 * gt)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("boxname", ["none", "ortho", "triclinic"])
+def test_shortest_distance(precision, boxname):
+    rng = np.random.default_rng(16)
+    box = BOXES[boxname]
+    n = 300
+    system = helpers.make_system(n, rng)
+    x = frames(rng, 4, n)
+    cv = cvpack.ShortestDistance(range(0, 100), range(150, 300), n, beta=100, pbc=box is not None)
+    run(cv, system, x, box, precision)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("boxname", ["none", "ortho"])
+@pytest.mark.parametrize("hydrogens,weigh", [(True, True), (False, False)])
+def test_residue_coordination(precision, boxname, hydrogens, weigh):
+    rng = np.random.default_rng(17)
+    box = BOXES[boxname]
+    topology = helpers.make_peptide(40, glycines=(3, 17))
+    n = topology.getNumAtoms()
+    system = helpers.make_system(n, rng)
+    x = frames(rng, 3, n)
+    residues = list(topology.residues())
+    cv = cvpack.ResidueCoordination(
+        residues[:15], residues[20:], pbc=box is not None, thresholdDistance=0.8,
+        normalize=True, weighByMass=weigh, includeHydrogens=hydrogens,
+    )
+    run(cv, system, x, box, precision)
+    assert cv.getReferenceValue()._value == 15 * 20
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_rmsd(precision):
+    """The scipy check of tests/test_cvpack.py:275-338 (full / half / shuffled groups)."""
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.default_rng(18)
+    n = 200
+    system = helpers.make_system(n, rng)
+    reference = rng.normal(size=(n, 3))
+    rot = Rotation.random(5, random_state=3).as_matrix()
+    x = np.einsum("bij,nj->bni", rot, reference) + 0.05 * rng.normal(size=(5, n, 3)) + 7.0
+    for group in (np.arange(n), np.arange(n // 2), rng.permutation(n)[: n // 2]):
+        for as_dict in (False, True):
+            ref = dict(zip(group.tolist(), reference[group])) if as_dict else reference
+            cv = cvpack.RMSD(ref, group, n)
+            ctx = run(cv, system, x, None, precision)
+            value = cv.getValue(ctx)._value.double().cpu().numpy()
+            stored = ctx.getPositions().double().cpu().numpy()
+            for b in range(5):
+                xs = stored[b][group] - stored[b][group].mean(0)
+                ys = reference[group] - reference[group].mean(0)
+                _, rssd = Rotation.align_vectors(xs, ys)
+                assert value[b] == pytest.approx(rssd / np.sqrt(len(group)), rel=TOL[precision][0] * 3)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_rmsd_degenerate(precision):
+    """msd < 1e-20 -> value 0 and zero gradient (OpenMM RMSDForce); FP32 noise keeps it ~0."""
+    rng = np.random.default_rng(19)
+    n = 64
+    system = helpers.make_system(n, rng)
+    reference = rng.normal(size=(n, 3))
+    cv = cvpack.RMSD(reference, range(n), n)
+    cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, reference[None], precision=precision)
+    value, grad = cv.getValueAndGradient(ctx)
+    assert float(value._value[0]) < (1e-3 if precision == "single" else 1e-7)
+    assert np.isfinite(grad.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_composite_rmsd(precision):
+    rng = np.random.default_rng(20)
+    n = 260
+    system = helpers.make_system(n, rng)
+    reference = rng.normal(size=(n, 3))
+    groups = [list(range(0, 90)), list(rng.permutation(np.arange(100, 220))[:70]), [230, 231, 240]]
+    x = reference[None] + 0.05 * rng.normal(size=(4, n, 3))
+    x[:, groups[1]] += 1.0  # translating one body must not matter (composite_rmsd.py:116-121)
+    cv = cvpack.CompositeRMSD(reference, groups, n)
+    ctx = run(cv, system, x, None, precision)
+    # doctest invariance: 0.0 at the reference, still 0.0 after translating one body by 1 nm
+    moved = reference.copy()
+    moved[groups[1]] += 1.0
+    ctx.setPositions(np.stack([reference, moved]))
+    value = cv.getValue(ctx)._value.cpu().numpy()
+    assert np.all(np.abs(value) < (2e-3 if precision == "single" else 1e-7))
+    with pytest.raises(ValueError):
+        cvpack.CompositeRMSD(reference, [[0, 1, 2], [2, 3, 4]], n)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_helix_rmsd_content(precision, normalize):
+    rng = np.random.default_rng(21)
+    topology = helpers.make_peptide(14, glycines=(4,))
+    n = topology.getNumAtoms()
+    system = helpers.make_system(n, rng)
+    base = helpers.ideal_helix_positions(14, rng)
+    x = base[None] + rng.normal(scale=0.02, size=(4, n, 3))
+    cv = cvpack.HelixRMSDContent(list(topology.residues()), n, normalize=normalize)
+    assert cv.getNumResidueBlocks() == 9
+    run(cv, system, x, None, precision)
+    # ideal coordinates: every block has rmsd ~ 0 -> S = 1 per block
+    cv2 = cvpack.HelixRMSDContent(list(topology.residues()), n)
+    cv2.addToSystem(system)
+    ctx = cvpack.BatchContext(system, base[None], precision=precision)
+    assert float(cv2.getValue(ctx)._value[0]) == pytest.approx(9.0, rel=2e-3)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("parallel", [False, True])
+def test_sheet_rmsd_content(precision, parallel):
+    rng = np.random.default_rng(22)
+    topology = helpers.make_peptide(12)
+    n = topology.getNumAtoms()
+    system = helpers.make_system(n, rng)
+    x = frames(rng, 3, n, scale=0.8)
+    cv = cvpack.SheetRMSDContent(list(topology.residues()), n, parallel=parallel, thresholdRMSD=0.5)
+    run(cv, system, x, None, precision)
+    cv = cvpack.SheetRMSDContent(list(topology.residues()), n, parallel=parallel, blockSizes=[6, 6], thresholdRMSD=0.5)
+    run(cv, system, x, None, precision)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("metric", ["progress", "deviation"])
+def test_path_in_rmsd_space(precision, metric):
+    rng = np.random.default_rng(23)
+    n = 150
+    system = helpers.make_system(n, rng)
+    start, end = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    atoms = rng.permutation(n)[:100]
+    milestones = []
+    for k in range(7):
+        conf = start + (end - start) * k / 6
+        order = rng.permutation(atoms) if k % 2 else atoms  # each milestone keeps its own order
+        milestones.append({int(a): conf[a] for a in order})
+    lam = np.linspace(0.1, 0.9, 5)[:, None, None]
+    x = start[None] + (end - start)[None] * lam + 0.02 * rng.normal(size=(5, n, 3))
+    cv = cvpack.PathInRMSDSpace(getattr(cvpack.path, metric), milestones, n, 0.3 * mmunit.nanometers)
+    assert cv.getName() == f"path_{metric}_in_rmsd_space"
+    vt, gt = TOL[precision]
+    helpers.check_against_oracle(cv, system, x, None, precision, 5 * vt, 5 * gt)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_helix_bonded_contents(precision, normalize):
+    rng = np.random.default_rng(24)
+    topology = helpers.make_peptide(16)
+    n = topology.getNumAtoms()
+    system = helpers.make_system(n, rng)
+    base = helpers.ideal_helix_positions(16, rng)
+    x = base[None] + rng.normal(scale=0.02, size=(4, n, 3))
+    residues = list(topology.residues())
+    run(cvpack.HelixTorsionContent(residues, normalize=normalize), system, x, None, precision)
+    run(cvpack.HelixAngleContent(residues, normalize=normalize), system, x, None, precision)
+    run(cvpack.HelixHBondContent(residues, normalize=normalize), system, x, None, precision)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_effective_mass_and_roundtrip(precision):
+    """perform_common_tests of the reference (tests/test_cvpack.py:52-88), batched."""
+    from oracle import cv_oracle
+
+    rng = np.random.default_rng(25)
+    n = 120
+    system = helpers.make_system(n, rng)
+    x = frames(rng, 6, n, scale=1.5)
+    nb = helpers.make_nonbonded(n, rng, periodic=False, num_exceptions=10)
+    cvs = [
+        cvpack.RadiusOfGyration(range(10, 90)),
+        cvpack.Torsion(1, 2, 3, 4),
+        cvpack.NumberOfContacts(range(0, 60), range(60, 120), nb),
+        cvpack.RMSD(x[0], range(0, 50), n),
+    ]
+    for cv in cvs:
+        cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, precision=precision)
+    for cv in cvs:
+        unity = 1 * cv.getUnit()
+        assert unity.value_in_unit_system(mmunit.md_unit_system) == 1
+        pipe = io.StringIO()
+        serialization.serialize(cv, pipe)
+        pipe.seek(0)
+        new_cv = serialization.deserialize(pipe)
+        new_cv.addToSystem(ctx.getSystem())
+        ctx.reinitialize(preserveState=True)
+        value1, value2 = cv.getValue(ctx), new_cv.getValue(ctx)
+        assert bool((value1 / value1.unit == value2 / value2.unit).all())  # bit-identical
+        mass1, mass2 = cv.getEffectiveMass(ctx), new_cv.getEffectiveMass(ctx)
+        assert bool((mass1 / mass1.unit == mass2 / mass2.unit).all())
+        assert cv.getName() == new_cv.getName()
+        assert cv.getPeriodicBounds() == new_cv.getPeriodicBounds()
+        grad = cv.getGradient(ctx).double().cpu().numpy()
+        emass = (mass1 / mass1.unit).double().cpu().numpy()
+        for b in range(x.shape[0]):
+            expected = cv_oracle.effective_mass(grad[b], system.getMasses())
+            assert emass[b] == pytest.approx(expected, rel=1e-5 if precision == "single" else 1e-12)
+
+
+def test_not_in_context_and_errors():
+    rng = np.random.default_rng(26)
+    system = helpers.make_system(30, rng)
+    ctx = cvpack.BatchContext(system, frames(rng, 2, 30))
+    cv = cvpack.RadiusOfGyration(range(30))
+    with pytest.raises(RuntimeError) as excinfo:
+        cv.getValue(ctx)
+    assert str(excinfo.value) == "This force is not present in the given context."
+    pbc_cv = cvpack.Distance(0, 1, pbc=True)
+    pbc_cv.addToSystem(system)
+    with pytest.raises(ValueError):
+        pbc_cv.getValue(ctx)  # periodic CV but no box
+
+
+def test_host_residency_matches_device():
+    rng = np.random.default_rng(27)
+    n = 500
+    system = helpers.make_system(n, rng)
+    x = frames(rng, 37, n)
+    nb = helpers.make_nonbonded(n, rng, periodic=True)
+    cv = cvpack.NumberOfContacts(range(0, 250), range(250, 500), nb)
+    cv.addToSystem(system)
+    dev = cvpack.BatchContext(system, x, ORTHO)
+    host = cvpack.BatchContext(system, x, ORTHO, residency="host")
+    v1, g1 = cv.getValueAndGradient(dev)
+    v2, g2 = cv.getValueAndGradient(host)
+    assert not v2._value.is_cuda and not g2.is_cuda
+    assert bool((v1._value.cpu() == v2._value).all())
+    assert bool((g1.cpu() == g2).all())
