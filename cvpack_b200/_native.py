@@ -147,6 +147,7 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     "cvp_launch_count": (C.c_int64, []),
     "cvp_set_workspace_limit": (C.c_int, [_vp, C.c_int64]),
     "cvp_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "cvp_get_stat": (C.c_int, [_vp, C.c_char_p, _f64p]),
     "cvp_measure_fp32_peak": (C.c_int, [C.c_int, _f64p]),
 }
 
@@ -251,6 +252,12 @@ class NativeCV:
     def set_option(self, name: str, value: int) -> int:
         """Set a per-family tuning switch; returns the previous value (or -1 if unknown)."""
         return load().cvp_set_option(self._handle, name.encode(), int(value))
+
+    def kernel_time(self, kernel: str) -> t.Tuple[float, int]:
+        """(device milliseconds, launches) of a named kernel since the last query."""
+        out = (C.c_double * 2)()
+        check(load().cvp_get_stat(self._handle, f"{kernel}_ms".encode(), out))
+        return float(out[0]), int(out[1])
 
     def evaluate(  # pylint: disable=too-many-arguments
         self,

@@ -215,7 +215,11 @@ class BatchContext:
             )
 
     def _run(
-        self, cv: t.Any, need_gradient: bool, positions: t.Optional[torch.Tensor] = None
+        self,
+        cv: t.Any,
+        need_gradient: bool,
+        positions: t.Optional[torch.Tensor] = None,
+        out: t.Optional[t.Tuple[torch.Tensor, t.Optional[torch.Tensor]]] = None,
     ) -> t.Tuple[torch.Tensor, t.Optional[torch.Tensor]]:
         self._require_cuda()
         pos = self.getPositions() if positions is None else positions
@@ -229,13 +233,18 @@ class BatchContext:
                 raise ValueError("the number of boxes differs from the number of frames")
             box_ptr = self._box[:num_frames].contiguous().data_ptr()
         on_host = self._residency == "host" and positions is None
+        if out is not None:
+            self._check_out(out, num_frames, num_atoms, need_gradient, on_host)
         if on_host:
-            value = torch.empty(num_frames, dtype=self._torch_dtype, pin_memory=True)
-            grad = (
-                torch.empty((num_frames, num_atoms, 3), dtype=self._torch_dtype, pin_memory=True)
-                if need_gradient
-                else None
-            )
+            if out is not None:
+                value, grad = out
+            else:
+                value = torch.empty(num_frames, dtype=self._torch_dtype, pin_memory=True)
+                grad = (
+                    torch.empty((num_frames, num_atoms, 3), dtype=self._torch_dtype, pin_memory=True)
+                    if need_gradient
+                    else None
+                )
             native.evaluate_host(
                 self._cvp_dtype, pos.data_ptr(), box_ptr, box_mode, num_frames, num_atoms,
                 value.data_ptr(), None if grad is None else grad.data_ptr(), flags,
@@ -248,12 +257,17 @@ class BatchContext:
             if box is not None and not box.is_cuda:
                 box = box.to(self._device)
                 box_ptr = box.data_ptr()
-            value = torch.empty(num_frames, dtype=self._torch_dtype, device=self._device)
-            grad = (
-                torch.empty((num_frames, num_atoms, 3), dtype=self._torch_dtype, device=self._device)
-                if need_gradient
-                else None
-            )
+            if out is not None:
+                value, grad = out
+            else:
+                value = torch.empty(num_frames, dtype=self._torch_dtype, device=self._device)
+                grad = (
+                    torch.empty(
+                        (num_frames, num_atoms, 3), dtype=self._torch_dtype, device=self._device
+                    )
+                    if need_gradient
+                    else None
+                )
             stream = torch.cuda.current_stream(self._device).cuda_stream
             native.evaluate(
                 self._cvp_dtype, pos.data_ptr(), box_ptr, box_mode, num_frames, num_atoms,
@@ -261,10 +275,42 @@ class BatchContext:
             )
         return value, grad
 
+    def _check_out(
+        self,
+        out: t.Tuple[torch.Tensor, t.Optional[torch.Tensor]],
+        num_frames: int,
+        num_atoms: int,
+        need_gradient: bool,
+        on_host: bool,
+    ) -> None:
+        value, grad = out
+        tensors = [(value, (num_frames,))]
+        if need_gradient:
+            if grad is None:
+                raise ValueError("a gradient buffer is required")
+            tensors.append((grad, (num_frames, num_atoms, 3)))
+        for tensor, shape in tensors:
+            if tuple(tensor.shape) != shape or tensor.dtype != self._torch_dtype:
+                raise ValueError(f"output buffer must have shape {shape} and dtype {self._torch_dtype}")
+            if not tensor.is_contiguous() or tensor.is_cuda == on_host:
+                raise ValueError("output buffers must be contiguous and live where the positions do")
+
     def _evaluate(
         self, cv: t.Any, need_gradient: bool
     ) -> t.Tuple[torch.Tensor, t.Optional[torch.Tensor]]:
         return self._run(cv, need_gradient)
+
+    def evaluateInto(
+        self, cv: t.Any, value: torch.Tensor, gradient: t.Optional[torch.Tensor] = None
+    ) -> None:
+        """
+        Evaluate a CV of this context's system into caller-owned buffers (``value`` ``[B]`` and,
+        optionally, ``gradient`` ``[B, N, 3]``; CUDA tensors for device residency, pinned CPU
+        tensors for host residency).  Lets a loop over trajectory chunks reuse its buffers.
+        """
+        if not any(force is cv for force in self._system.getForces()):
+            raise RuntimeError("This force is not present in the given context.")
+        self._run(cv, gradient is not None, out=(value, gradient))
 
     def _evaluateDetached(self, cv: t.Any) -> float:
         """Value of a CV (not necessarily in the system) at the first frame."""

@@ -272,6 +272,13 @@ int cvp_set_option(cvp_cv* cv, const char* name, int value) {
   return cv->set_option(name, value);
 }
 
+int cvp_get_stat(cvp_cv* cv, const char* name, double* out) {
+  CVP_REQUIRE(cv != nullptr && name != nullptr && out != nullptr, "null argument");
+  int status = cv->get_stat(name, out);
+  if (status != CVP_OK) set_error(std::string("unknown statistic: ") + name);
+  return status;
+}
+
 int cvp_measure_fp32_peak(int device, double* tflops) {
   CVP_REQUIRE(tflops != nullptr, "null argument");
   CVP_CUDA_CHECK(cudaSetDevice(device));

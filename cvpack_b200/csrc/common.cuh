@@ -105,13 +105,69 @@ struct EvalArgs {
 
 }  // namespace cvp
 
+namespace cvp {
+// Optional per-kernel device timing (CUDA events on the launching stream), switched on with
+// cvp_set_option(cv, "time_kernels", 1) and read back with cvp_get_stat(cv, "<kernel>_ms", ...).
+struct KernelTimer {
+  struct Span {
+    std::string name;
+    cudaEvent_t start, stop;
+  };
+  bool enabled = false;
+  std::vector<Span> spans;
+  void begin(const char* name, cudaStream_t stream) {
+    if (!enabled) return;
+    Span span{name, nullptr, nullptr};
+    cudaEventCreate(&span.start);
+    cudaEventCreate(&span.stop);
+    cudaEventRecord(span.start, stream);
+    spans.push_back(span);
+  }
+  void end(cudaStream_t stream) {
+    if (!enabled || spans.empty()) return;
+    cudaEventRecord(spans.back().stop, stream);
+  }
+  // total milliseconds and number of spans recorded under `name`; consumes them
+  void collect(const std::string& name, double* ms, double* count) {
+    *ms = 0.0;
+    *count = 0.0;
+    std::vector<Span> keep;
+    for (auto& span : spans) {
+      if (span.name != name) {
+        keep.push_back(span);
+        continue;
+      }
+      cudaEventSynchronize(span.stop);
+      float elapsed = 0.f;
+      cudaEventElapsedTime(&elapsed, span.start, span.stop);
+      *ms += elapsed;
+      *count += 1.0;
+      cudaEventDestroy(span.start);
+      cudaEventDestroy(span.stop);
+    }
+    spans.swap(keep);
+  }
+  void clear() {
+    for (auto& span : spans) {
+      cudaEventDestroy(span.start);
+      cudaEventDestroy(span.stop);
+    }
+    spans.clear();
+  }
+};
+}  // namespace cvp
+
 struct cvp_cv {
   int num_atoms = 0;
+  cvp::KernelTimer timer;
   int device = -1;  // device the spec's arrays live on (-1: not uploaded yet)
   int64_t workspace_limit = int64_t(1) << 30;
   std::vector<int32_t> active_atoms;  // sorted, unique
   cvp::DeviceBuffer workspace;
-  virtual ~cvp_cv() { workspace.release(); }
+  virtual ~cvp_cv() {
+    timer.clear();
+    workspace.release();
+  }
   // Upload index/parameter arrays to the current device.
   virtual int upload() = 0;
   // Workspace bytes needed per frame and independent of the frame count.
@@ -122,9 +178,29 @@ struct cvp_cv {
   // Evaluate frames [0, args.num_frames) of the given (already offset) pointers.
   virtual int run(const cvp::EvalArgs& args, void* workspace) = 0;
   virtual int set_option(const char* name, int value) {
-    (void)name;
-    (void)value;
+    if (std::string(name) == "time_kernels") {
+      int previous = timer.enabled ? 1 : 0;
+      timer.enabled = value != 0;
+      if (!timer.enabled) timer.clear();
+      return previous;
+    }
     return -1;
+  }
+  // Named statistics: "<kernel>_ms" / "<kernel>_launches" from the kernel timer.
+  virtual int get_stat(const char* name, double* out) {
+    std::string key(name);
+    double ms = 0.0, count = 0.0;
+    auto ends_with = [&](const std::string& suffix) {
+      return key.size() > suffix.size() &&
+             key.compare(key.size() - suffix.size(), suffix.size(), suffix) == 0;
+    };
+    if (ends_with("_ms")) {
+      timer.collect(key.substr(0, key.size() - 3), &ms, &count);
+      out[0] = ms;
+      out[1] = count;
+      return CVP_OK;
+    }
+    return CVP_ERR_INVALID;
   }
 };
 

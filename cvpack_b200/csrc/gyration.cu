@@ -244,7 +244,9 @@ struct GyrationCV : cvp_cv {
     const unsigned grid = (unsigned)(B * ns);
     const int warp_blocks = (int)div_up(B * 32, 128);
 
+    timer.begin("gyration_sums", st);
     gyration_sums_kernel<T><<<grid, GYR_THREADS, 0, st>>>(pos, N, idx, w, n, first, ns, partials);
+    timer.end(st);
     CVP_LAUNCH_CHECK();
     gyration_centre_kernel<T><<<warp_blocks, 128, 0, st>>>(partials, ns, n, PBC != 0, squared, rec,
                                                             value, accumulate ? 1 : 0, B);
@@ -261,8 +263,10 @@ struct GyrationCV : cvp_cv {
     const bool dense = contiguous && n == N;
     if (!accumulate && !dense)
       CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+    timer.begin("gyration_gradient", st);
     gyration_gradient_kernel<T, PBC><<<grid, GYR_THREADS, 0, st>>>(
         pos, N, idx, w, n, first, ns, box, a.box_mode, rec, grad, accumulate ? 1 : 0);
+    timer.end(st);
     CVP_LAUNCH_CHECK();
     return CVP_OK;
   }

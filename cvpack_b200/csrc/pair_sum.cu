@@ -620,38 +620,42 @@ struct PairSumCV : cvp_cv {
     const unsigned grid1 = (unsigned)(B * nb1), grid2 = (unsigned)(B * nb2);
     const int finish_blocks = (int)div_up(B * 32, 128);
 
+    // one sweep: `first` selects which group sits in registers (true: group1 over group2)
+    auto sweep = [&](bool first, bool with_grad, const T* coef, double* energy) -> int {
+      const T4* ip = first ? p1 : p2;
+      const T4* jp = first ? p2 : p1;
+      const T4* iq = first ? prm1 : prm2;
+      const T4* jq = first ? prm2 : prm1;
+      const int ni = first ? n1 : n2, nj = first ? n2 : n1, nbi = first ? nb1 : nb2;
+      T4* out = first ? gr1 : gr2;
+      timer.begin("sweep", st);
+      if (with_grad)
+        pair_sweep_kernel<T, KIND, PBC, OVERLAP, true><<<first ? grid1 : grid2, PAIR_THREADS, 0, st>>>(
+            ip, jp, iq, jq, ni, nj, nbi, box, a.box_mode, pc, coef, energy, out);
+      else
+        pair_sweep_kernel<T, KIND, PBC, OVERLAP, false><<<first ? grid1 : grid2, PAIR_THREADS, 0, st>>>(
+            ip, jp, iq, jq, ni, nj, nbi, box, a.box_mode, pc, coef, energy, nullptr);
+      timer.end(st);
+      CVP_LAUNCH_CHECK();
+      return CVP_OK;
+    };
+    int status;
     if (KIND == CVP_PAIR_SOFTMIN) {
       // value pass first: the gradient of a ratio of sums needs the sums
-      pair_sweep_kernel<T, KIND, PBC, OVERLAP, false><<<grid1, PAIR_THREADS, 0, st>>>(
-          p1, p2, prm1, prm2, n1, n2, nb1, box, a.box_mode, pc, nullptr, partials, nullptr);
-      CVP_LAUNCH_CHECK();
+      if ((status = sweep(true, false, nullptr, partials)) != CVP_OK) return status;
       pair_finish_kernel<T, KIND><<<finish_blocks, 128, 0, st>>>(
           partials, nb1, nullptr, 1.0, rc, exp_neg_beta, value, frame_coef, accumulate ? 1 : 0, B);
       CVP_LAUNCH_CHECK();
-      if (need_grad) {
-        pair_sweep_kernel<T, KIND, PBC, OVERLAP, true><<<grid1, PAIR_THREADS, 0, st>>>(
-            p1, p2, prm1, prm2, n1, n2, nb1, box, a.box_mode, pc, frame_coef, nullptr, gr1);
-        CVP_LAUNCH_CHECK();
-      }
+      if (need_grad && (status = sweep(true, true, frame_coef, nullptr)) != CVP_OK) return status;
     } else {
-      if (need_grad) {
-        pair_sweep_kernel<T, KIND, PBC, OVERLAP, true><<<grid1, PAIR_THREADS, 0, st>>>(
-            p1, p2, prm1, prm2, n1, n2, nb1, box, a.box_mode, pc, nullptr, partials, gr1);
-      } else {
-        pair_sweep_kernel<T, KIND, PBC, OVERLAP, false><<<grid1, PAIR_THREADS, 0, st>>>(
-            p1, p2, prm1, prm2, n1, n2, nb1, box, a.box_mode, pc, nullptr, partials, nullptr);
-      }
-      CVP_LAUNCH_CHECK();
+      if ((status = sweep(true, need_grad, nullptr, partials)) != CVP_OK) return status;
       pair_finish_kernel<T, KIND><<<finish_blocks, 128, 0, st>>>(
           partials, nb1, has_ex ? excluded : nullptr, d.scale, rc, exp_neg_beta, value, nullptr,
           accumulate ? 1 : 0, B);
       CVP_LAUNCH_CHECK();
     }
     if (!need_grad) return CVP_OK;
-
-    pair_sweep_kernel<T, KIND, PBC, OVERLAP, true><<<grid2, PAIR_THREADS, 0, st>>>(
-        p2, p1, prm2, prm1, n2, n1, nb2, box, a.box_mode, pc, frame_coef, nullptr, gr2);
-    CVP_LAUNCH_CHECK();
+    if ((status = sweep(false, true, frame_coef, nullptr)) != CVP_OK) return status;
 
     if (!accumulate)
       CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
@@ -957,19 +961,23 @@ struct CentroidPairSumCV : cvp_cv {
         n2, p1, p2, total);
     CVP_LAUNCH_CHECK();
     const unsigned grid1 = (unsigned)(B * nb1), grid2 = (unsigned)(B * nb2);
+    timer.begin("sweep", st);
     if (need_grad)
       pair_sweep_kernel<T, KIND, PBC, false, true><<<grid1, PAIR_THREADS, 0, st>>>(
           p1, p2, nullptr, nullptr, n1, n2, nb1, box, a.box_mode, pc, nullptr, partials, gr1);
     else
       pair_sweep_kernel<T, KIND, PBC, false, false><<<grid1, PAIR_THREADS, 0, st>>>(
           p1, p2, nullptr, nullptr, n1, n2, nb1, box, a.box_mode, pc, nullptr, partials, nullptr);
+    timer.end(st);
     CVP_LAUNCH_CHECK();
     pair_finish_kernel<T, KIND><<<(unsigned)div_up(B * 32, 128), 128, 0, st>>>(
         partials, nb1, nullptr, d.scale, 0.0, 0.0, value, nullptr, accumulate ? 1 : 0, B);
     CVP_LAUNCH_CHECK();
     if (!need_grad) return CVP_OK;
+    timer.begin("sweep", st);
     pair_sweep_kernel<T, KIND, PBC, false, true><<<grid2, PAIR_THREADS, 0, st>>>(
         p2, p1, nullptr, nullptr, n2, n1, nb2, box, a.box_mode, pc, nullptr, nullptr, gr2);
+    timer.end(st);
     CVP_LAUNCH_CHECK();
     if (!accumulate) CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
     const int num_active = (int)active_atoms.size();

@@ -367,10 +367,12 @@ struct RmsdCV : cvp_cv {
 
     {
       int64_t warps = B * nslice;
+      timer.begin("rmsd_sums", st);
       rmsd_sums_kernel<T><<<(unsigned)div_up(warps, RMSD_WARPS), RMSD_WARPS * 32, 0, st>>>(
           pos, N, static_cast<const int32_t*>(d_entry_atom.ptr),
           static_cast<const double*>(d_ref.ptr), static_cast<const RmsdSlice*>(d_slices.ptr),
           nslice, B, partials);
+      timer.end(st);
       CVP_LAUNCH_CHECK();
     }
     {
@@ -393,6 +395,7 @@ struct RmsdCV : cvp_cv {
     {
       const int num_active = (int)active_atoms.size();
       int64_t total = B * (int64_t)num_active;
+      timer.begin("rmsd_gradient", st);
       rmsd_gradient_kernel<T><<<(unsigned)div_up(total, 256), 256, 0, st>>>(
           pos, N, static_cast<const int32_t*>(d_active.ptr),
           static_cast<const int32_t*>(d_atom_entry_offsets.ptr),
@@ -400,6 +403,7 @@ struct RmsdCV : cvp_cv {
           static_cast<const int32_t*>(d_entry_group.ptr),
           static_cast<const int32_t*>(d_entry_seg.ptr), static_cast<const double*>(d_ref.ptr),
           solution, seg_centroid, group_factor, num_groups, nseg, grad, accumulate ? 1 : 0, total);
+      timer.end(st);
       CVP_LAUNCH_CHECK();
     }
     return CVP_OK;

@@ -220,6 +220,11 @@ int64_t cvp_launch_count(void);
 int cvp_set_workspace_limit(cvp_cv* cv, int64_t bytes);
 /* Per-family tuning switch (meaning documented in DESIGN.md); returns previous value.            */
 int cvp_set_option(cvp_cv* cv, const char* name, int value);
+/* Named statistic of a spec.  "<kernel>_ms" -> out[0] = device milliseconds spent in that kernel
+ * since the last query (CUDA events on the launching stream; needs option "time_kernels" = 1),
+ * out[1] = number of launches.  Kernel names: "sweep" (pair sums), "rmsd_sums", "rmsd_gradient",
+ * "gyration_sums", "gyration_gradient".                                                         */
+int cvp_get_stat(cvp_cv* cv, const char* name, double* out);
 /* Sustained FP32 FMA throughput of `device` in TFLOP/s measured by a register-resident FFMA loop
  * (the FP32 roofline denominator of the pair kernels).                                           */
 int cvp_measure_fp32_peak(int device, double* tflops);
