@@ -1,0 +1,148 @@
+// Device-side building blocks shared by the pair-sum kernels: per-pair functions (energy and
+// (dE/dr)/r), switching, minimum image, tags.
+#pragma once
+
+#include "common.cuh"
+
+namespace cvp {
+namespace {
+
+template <typename T>
+struct PairConsts {
+  T cutoff2;    // squared cutoff (huge if none)
+  T rs;         // switching distance
+  T inv_range;  // 1/(rc - rs)
+  int has_switch;
+  T inv_r0;
+  StepParams step;
+  T inv_rc;     // attraction: x = r/rc
+  T ke;         // attraction: Coulomb constant
+  double neg_beta_over_rc;  // softmin
+};
+
+// ---- tags: atom index (+ "member of both groups" flag) carried in the w lane, bit-exact ---------
+__device__ __forceinline__ float tag_encode(int tag, float) { return __int_as_float(tag); }
+__device__ __forceinline__ double tag_encode(int tag, double) {
+  return __longlong_as_double((long long)tag);
+}
+__device__ __forceinline__ int tag_decode(float w) { return __float_as_int(w); }
+__device__ __forceinline__ int tag_decode(double w) { return (int)__double_as_longlong(w); }
+constexpr int TAG_BOTH = 0x40000000;  // set when the atom belongs to both groups
+constexpr int TAG_INDEX_MASK = 0x3fffffff;
+
+template <typename T>
+__device__ __forceinline__ T round_nearest(T x);
+template <>
+__device__ __forceinline__ float round_nearest<float>(float x) {
+  // round-to-nearest-even through the 1.5*2^23 magic constant: two full-rate FADDs instead of
+  // the quarter-rate FRND; valid for |x| < 2^22, far beyond any image count
+  return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f);
+}
+template <>
+__device__ __forceinline__ double round_nearest<double>(double x) {
+  return rint(x);
+}
+
+template <int PBC, typename T>
+__device__ __forceinline__ void pair_min_image(T& dx, T& dy, T& dz, const Box<T>& box) {
+  if (PBC == 1) {
+    dx = fma(-box.ax, round_nearest(dx * box.inv_ax), dx);
+    dy = fma(-box.by, round_nearest(dy * box.inv_by), dy);
+    dz = fma(-box.cz, round_nearest(dz * box.inv_cz), dz);
+  } else if (PBC == 2) {
+    min_image<2>(dx, dy, dz, box);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void switching(const PairConsts<T>& pc, T r, T& e, T& de) {
+  if (pc.has_switch && r > pc.rs) {
+    T t = (r - pc.rs) * pc.inv_range;
+    T sw = T(1) + t * t * t * (T(-10) + t * (T(15) - T(6) * t));
+    T dsw = t * t * (T(-30) + t * (T(60) - T(30) * t)) * pc.inv_range;
+    de = de * sw + e * dsw;
+    e = e * sw;
+  }
+}
+
+// ---- pair functions: energy e and coef = (de/dr)/r for a pair at squared distance r2 -----------
+template <typename T, int KIND>
+struct PairFn;
+
+template <typename T>
+struct PairFn<T, CVP_PAIR_CONTACTS> {
+  using T4 = typename Vec4<T>::type;
+  static constexpr int NCH = 1;
+  static constexpr bool HAS_PARAMS = false;
+  __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4&, const T4&,
+                                              const T*, T (&e)[1], T& coef) {
+    T inv_r = rsqrt_t(r2);
+    T r = r2 * inv_r;
+    T s, ds;
+    step_function(pc.step, r * pc.inv_r0, s, ds);
+    T de = ds * pc.inv_r0;
+    switching(pc, r, s, de);
+    e[0] = s;
+    coef = de * inv_r;
+  }
+};
+
+template <typename T>
+struct PairFn<T, CVP_PAIR_ATTRACTION> {
+  using T4 = typename Vec4<T>::type;
+  static constexpr int NCH = 1;
+  static constexpr bool HAS_PARAMS = true;
+  // params: x = charge, y = sigma, z = epsilon, w = sign
+  __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4& pi,
+                                              const T4& pj, const T*, T (&e)[1], T& coef) {
+    T inv_r = rsqrt_t(r2);
+    T r = r2 * inv_r;
+    T sigma = T(0.5) * (pi.y + pj.y);
+    T epsilon = sqrt_t(pi.z * pj.z);
+    T qq = fmin(T(0), pi.x * pj.x);
+    T sgn = pi.w * pj.w;
+    T u = r / sigma;
+    T u2 = u * u;
+    T u6 = u2 * u2 * u2;
+    T a = u6 - T(2);
+    T y = fabs(a) + T(2);
+    T inv_y = T(1) / y;
+    T lj = T(4) * epsilon * (inv_y * inv_y - inv_y);
+    // d|a|/da = +1 at a == 0 (Lepton: 2*step(a)-1)
+    T dy = (a >= T(0) ? T(6) : T(-6)) * u6 * inv_r;
+    T dlj = T(4) * epsilon * (T(-2) * inv_y * inv_y * inv_y + inv_y * inv_y) * dy;
+    T x = r * pc.inv_rc;
+    T coul = pc.ke * qq * (T(1) / x + T(0.5) * (x * x - T(3)));
+    T dcoul = pc.ke * qq * (T(-1) / (x * x) + x) * pc.inv_rc;
+    T en = -sgn * (lj + coul);
+    T de = -sgn * (dlj + dcoul);
+    switching(pc, r, en, de);
+    e[0] = en;
+    coef = de * inv_r;
+  }
+};
+
+template <typename T>
+struct PairFn<T, CVP_PAIR_SOFTMIN> {
+  using T4 = typename Vec4<T>::type;
+  static constexpr int NCH = 2;
+  static constexpr bool HAS_PARAMS = false;
+  // channels: sum r w and sum w, w = exp(-beta r/rc); gradient pass uses per-frame c = {1/D, -rmin/D}
+  __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4&, const T4&,
+                                              const T* c, T (&e)[2], T& coef) {
+    double r = sqrt((double)r2);
+    double w = exp(pc.neg_beta_over_rc * r);
+    e[0] = T(r * w);
+    e[1] = T(w);
+    if (c != nullptr) {
+      // w and r w can underflow T; the normalised product w/D cannot overflow (w/D <= 1)
+      double dw = pc.neg_beta_over_rc * w;
+      coef = T(((double)c[0] * (w + r * dw) + (double)c[1] * dw) / r);
+    } else {
+      coef = T(0);
+    }
+  }
+};
+
+}  // namespace
+}  // namespace cvp

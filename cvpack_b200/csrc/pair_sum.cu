@@ -11,7 +11,8 @@
 //   3. sweep B   roles swapped: gradients of group2 atoms (skipped for value-only calls)
 //   4. finish    deterministic reduction of the per-block energy partials, exclusions, scaling
 //   5. scatter   packed gradients -> [B][N][3]
-#include "common.cuh"
+#include "pair_common.cuh"
+#include "pair_cells.cuh"
 
 namespace cvp {
 
@@ -21,143 +22,6 @@ constexpr int PAIR_THREADS = 128;
 constexpr int PAIR_IPT = 2;      // i atoms per thread
 constexpr int PAIR_TILE = 256;   // j atoms per shared-memory stage
 constexpr int PAIR_I_PER_BLOCK = PAIR_THREADS * PAIR_IPT;
-
-template <typename T>
-struct PairConsts {
-  T cutoff2;    // squared cutoff (huge if none)
-  T rs;         // switching distance
-  T inv_range;  // 1/(rc - rs)
-  int has_switch;
-  T inv_r0;
-  StepParams step;
-  T inv_rc;     // attraction: x = r/rc
-  T ke;         // attraction: Coulomb constant
-  double neg_beta_over_rc;  // softmin
-};
-
-// ---- tags: atom index (+ "member of both groups" flag) carried in the w lane, bit-exact ---------
-__device__ __forceinline__ float tag_encode(int tag, float) { return __int_as_float(tag); }
-__device__ __forceinline__ double tag_encode(int tag, double) {
-  return __longlong_as_double((long long)tag);
-}
-__device__ __forceinline__ int tag_decode(float w) { return __float_as_int(w); }
-__device__ __forceinline__ int tag_decode(double w) { return (int)__double_as_longlong(w); }
-constexpr int TAG_BOTH = 0x40000000;  // set when the atom belongs to both groups
-constexpr int TAG_INDEX_MASK = 0x3fffffff;
-
-template <typename T>
-__device__ __forceinline__ T round_nearest(T x);
-template <>
-__device__ __forceinline__ float round_nearest<float>(float x) {
-  // round-to-nearest-even through the 1.5*2^23 magic constant: two full-rate FADDs instead of
-  // the quarter-rate FRND; valid for |x| < 2^22, far beyond any image count
-  return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f);
-}
-template <>
-__device__ __forceinline__ double round_nearest<double>(double x) {
-  return rint(x);
-}
-
-template <int PBC, typename T>
-__device__ __forceinline__ void pair_min_image(T& dx, T& dy, T& dz, const Box<T>& box) {
-  if (PBC == 1) {
-    dx = fma(-box.ax, round_nearest(dx * box.inv_ax), dx);
-    dy = fma(-box.by, round_nearest(dy * box.inv_by), dy);
-    dz = fma(-box.cz, round_nearest(dz * box.inv_cz), dz);
-  } else if (PBC == 2) {
-    min_image<2>(dx, dy, dz, box);
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ void switching(const PairConsts<T>& pc, T r, T& e, T& de) {
-  if (pc.has_switch && r > pc.rs) {
-    T t = (r - pc.rs) * pc.inv_range;
-    T sw = T(1) + t * t * t * (T(-10) + t * (T(15) - T(6) * t));
-    T dsw = t * t * (T(-30) + t * (T(60) - T(30) * t)) * pc.inv_range;
-    de = de * sw + e * dsw;
-    e = e * sw;
-  }
-}
-
-// ---- pair functions: energy e and coef = (de/dr)/r for a pair at squared distance r2 -----------
-template <typename T, int KIND>
-struct PairFn;
-
-template <typename T>
-struct PairFn<T, CVP_PAIR_CONTACTS> {
-  using T4 = typename Vec4<T>::type;
-  static constexpr int NCH = 1;
-  static constexpr bool HAS_PARAMS = false;
-  __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4&, const T4&,
-                                              const T*, T (&e)[1], T& coef) {
-    T inv_r = rsqrt_t(r2);
-    T r = r2 * inv_r;
-    T s, ds;
-    step_function(pc.step, r * pc.inv_r0, s, ds);
-    T de = ds * pc.inv_r0;
-    switching(pc, r, s, de);
-    e[0] = s;
-    coef = de * inv_r;
-  }
-};
-
-template <typename T>
-struct PairFn<T, CVP_PAIR_ATTRACTION> {
-  using T4 = typename Vec4<T>::type;
-  static constexpr int NCH = 1;
-  static constexpr bool HAS_PARAMS = true;
-  // params: x = charge, y = sigma, z = epsilon, w = sign
-  __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4& pi,
-                                              const T4& pj, const T*, T (&e)[1], T& coef) {
-    T inv_r = rsqrt_t(r2);
-    T r = r2 * inv_r;
-    T sigma = T(0.5) * (pi.y + pj.y);
-    T epsilon = sqrt_t(pi.z * pj.z);
-    T qq = fmin(T(0), pi.x * pj.x);
-    T sgn = pi.w * pj.w;
-    T u = r / sigma;
-    T u2 = u * u;
-    T u6 = u2 * u2 * u2;
-    T a = u6 - T(2);
-    T y = fabs(a) + T(2);
-    T inv_y = T(1) / y;
-    T lj = T(4) * epsilon * (inv_y * inv_y - inv_y);
-    // d|a|/da = +1 at a == 0 (Lepton: 2*step(a)-1)
-    T dy = (a >= T(0) ? T(6) : T(-6)) * u6 * inv_r;
-    T dlj = T(4) * epsilon * (T(-2) * inv_y * inv_y * inv_y + inv_y * inv_y) * dy;
-    T x = r * pc.inv_rc;
-    T coul = pc.ke * qq * (T(1) / x + T(0.5) * (x * x - T(3)));
-    T dcoul = pc.ke * qq * (T(-1) / (x * x) + x) * pc.inv_rc;
-    T en = -sgn * (lj + coul);
-    T de = -sgn * (dlj + dcoul);
-    switching(pc, r, en, de);
-    e[0] = en;
-    coef = de * inv_r;
-  }
-};
-
-template <typename T>
-struct PairFn<T, CVP_PAIR_SOFTMIN> {
-  using T4 = typename Vec4<T>::type;
-  static constexpr int NCH = 2;
-  static constexpr bool HAS_PARAMS = false;
-  // channels: sum r w and sum w, w = exp(-beta r/rc); gradient pass uses per-frame c = {1/D, -rmin/D}
-  __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4&, const T4&,
-                                              const T* c, T (&e)[2], T& coef) {
-    double r = sqrt((double)r2);
-    double w = exp(pc.neg_beta_over_rc * r);
-    e[0] = T(r * w);
-    e[1] = T(w);
-    if (c != nullptr) {
-      // w and r w can underflow T; the normalised product w/D cannot overflow (w/D <= 1)
-      double dw = pc.neg_beta_over_rc * w;
-      coef = T(((double)c[0] * (w + r * dw) + (double)c[1] * dw) / r);
-    } else {
-      coef = T(0);
-    }
-  }
-};
 
 // ---- 1. pack -----------------------------------------------------------------------------------
 template <typename T>
@@ -482,6 +346,8 @@ struct PairSumCV : cvp_cv {
   std::vector<double> charge, sigma, epsilon, sign;
   bool overlap = false;
   bool identical = false;  // group1 and group2 are the same set
+  int use_cells = 1;       // option "cells": 1 = cell-sorted fast path when eligible, 0 = all pairs
+  int nsplit_override = 0; // option "nsplit": CTAs per frame in the cell sweep (0 = automatic)
   DeviceBuffer d_g1, d_g2, d_tag1, d_tag2, d_ex_pairs, d_ex_atoms, d_ex_offsets, d_ex_partners;
   DeviceBuffer d_prm1[2], d_prm2[2], d_prm_atom[2];  // per dtype
 
@@ -533,12 +399,33 @@ struct PairSumCV : cvp_cv {
   size_t workspace_per_frame(int dtype, bool need_grad) const override {
     size_t rec = dtype == CVP_F32 ? 16 : 32;
     size_t real = dtype == CVP_F32 ? 4 : 8;
-    size_t n = g1.size() + g2.size();
-    size_t bytes = n * rec + 512;                                 // packed positions
-    if (need_grad) bytes += n * rec + 512;                        // packed gradients
-    bytes += (size_t)nblk((int)g1.size()) * 2 * sizeof(double);   // energy partials
-    bytes += sizeof(double) + 2 * real;                           // excluded energy, frame coef
+    // sized for the cell path (padded groups + cluster boxes), which also covers the all-pairs path
+    size_t n = cell_round_up((int)g1.size(), CELL_TILE) + cell_round_up((int)g2.size(), CELL_TILE);
+    size_t bytes = n * rec + 2 * (n / CELL_CLUSTER) * rec + 1024;  // positions + cluster boxes
+    if (need_grad) bytes += n * rec + 512;                         // packed gradients
+    bytes += (size_t)std::max(nblk((int)g1.size()), 64) * 2 * sizeof(double);  // energy partials
+    bytes += sizeof(double) + 2 * real;                            // excluded energy, frame coef
     return bytes;
+  }
+  int set_option(const char* name, int value) override {
+    const std::string key(name);
+    if (key == "cells") {
+      std::swap(use_cells, value);
+      return value;
+    }
+    if (key == "nsplit") {
+      std::swap(nsplit_override, value);
+      return value;
+    }
+    return cvp_cv::set_option(name, value);
+  }
+  size_t cell_sort_smem(int n) const {
+    return (size_t)(2 * CELL_MAX_CELLS + 1) * sizeof(int) + 2 * (size_t)cell_round_up(n, 8) * sizeof(uint16_t);
+  }
+  bool cells_eligible(int pbc) const {
+    const size_t limit = 200 * 1024;
+    return use_cells && d.cutoff > 0 && pbc != 2 && g1.size() <= 65535 && g2.size() <= 65535 &&
+           cell_sort_smem((int)std::max(g1.size(), g2.size())) <= limit;
   }
   size_t workspace_fixed(int) const override { return 8 * 256; }
   int64_t max_frames_per_run() const override {
@@ -565,8 +452,133 @@ struct PairSumCV : cvp_cv {
     return pc;
   }
 
+  // ---- cell-sorted fast path (pair_cells.cuh) ----
+  template <typename T, int KIND, int PBC, bool OVERLAP>
+  int run_cells(const EvalArgs& a, void* ws) {
+    using T4 = typename Vec4<T>::type;
+    constexpr int NCH = PairFn<T, KIND>::NCH;
+    constexpr int CPBC = PBC == 2 ? 0 : PBC;  // triclinic never gets here
+    const int which = std::is_same<T, float>::value ? 0 : 1;
+    const int64_t B = a.num_frames;
+    const int64_t N = a.num_atoms;
+    const int n1 = (int)g1.size(), n2 = (int)g2.size();
+    const int n1p = cell_round_up(n1, CELL_TILE), n2p = cell_round_up(n2, CELL_TILE);
+    const bool need_grad = a.grad != nullptr;
+    const bool accumulate = (a.flags & CVP_FLAG_ACCUMULATE) != 0;
+    const PairConsts<T> pc = consts<T>();
+    const T* pos = static_cast<const T*>(a.positions);
+    const T* box = static_cast<const T*>(a.box);
+    T* value = static_cast<T*>(a.value);
+    T* grad = static_cast<T*>(a.grad);
+    cudaStream_t st = a.stream;
+
+    int nsplit = nsplit_override;
+    if (nsplit <= 0) {
+      // enough CTAs for ~4 waves of 2 CTAs per SM, but never fewer tiles than warps per CTA
+      const int64_t want = 148 * 2 * 4;
+      nsplit = (int)std::max<int64_t>(1, div_up(want, B));
+      const int ntile = std::min(n1p, n2p) / CELL_TILE;
+      nsplit = std::max(1, std::min(nsplit, ntile / (CELL_SWEEP_THREADS / 32)));
+    }
+
+    Carver carve(ws);
+    T4* s1 = carve.take<T4>((size_t)B * n1p);
+    T4* s2 = carve.take<T4>((size_t)B * n2p);
+    T4* bb1 = carve.take<T4>((size_t)B * (n1p / CELL_CLUSTER) * 2);
+    T4* bb2 = carve.take<T4>((size_t)B * (n2p / CELL_CLUSTER) * 2);
+    T4* gr1 = need_grad ? carve.take<T4>((size_t)B * n1p) : nullptr;
+    T4* gr2 = need_grad ? carve.take<T4>((size_t)B * n2p) : nullptr;
+    double* partials = carve.take<double>((size_t)B * nsplit * NCH);
+    double* excluded = carve.take<double>((size_t)B);
+    T* frame_coef = carve.take<T>((size_t)B * 2);
+    const T4* prm_atom = static_cast<const T4*>(d_prm_atom[which].ptr);
+
+    {
+      const size_t smem = cell_sort_smem(std::max(n1, n2));
+      auto kernel = cell_sort_kernel<T, CPBC>;
+      CVP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      timer.begin("cell_sort", st);
+      kernel<<<(unsigned)(2 * B), CELL_SORT_THREADS, smem, st>>>(
+          pos, N, static_cast<const int32_t*>(d_g1.ptr), static_cast<const int32_t*>(d_tag1.ptr), n1,
+          n1p, static_cast<const int32_t*>(d_g2.ptr), static_cast<const int32_t*>(d_tag2.ptr), n2,
+          n2p, box, a.box_mode, s1, s2, bb1, bb2);
+      timer.end(st);
+      CVP_LAUNCH_CHECK();
+    }
+    const bool has_ex = !ex_pairs.empty() && KIND != CVP_PAIR_SOFTMIN;
+    if (has_ex) {
+      exclusion_energy_kernel<T, KIND, PBC><<<(unsigned)B, 128, 0, st>>>(
+          pos, N, prm_atom, static_cast<const int32_t*>(d_ex_pairs.ptr),
+          (int)(ex_pairs.size() / 2), box, a.box_mode, pc, excluded);
+      CVP_LAUNCH_CHECK();
+    }
+    const int jchunk = cell_jchunk<T>();
+    const size_t sweep_smem = (size_t)jchunk * sizeof(T4) + (size_t)(jchunk / CELL_CLUSTER) * 2 * sizeof(T4);
+    auto sweep = [&](bool first, bool with_grad, const T* coef, double* energy) -> int {
+      const T4* ip = first ? s1 : s2;
+      const T4* jp = first ? s2 : s1;
+      const T4* jb = first ? bb2 : bb1;
+      const int nip = first ? n1p : n2p, njp = first ? n2p : n1p;
+      T4* out = first ? gr1 : gr2;
+      auto kernel = with_grad ? cell_sweep_kernel<T, KIND, CPBC, OVERLAP, true>
+                              : cell_sweep_kernel<T, KIND, CPBC, OVERLAP, false>;
+      CVP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sweep_smem));
+      timer.begin("sweep", st);
+      kernel<<<(unsigned)(B * nsplit), CELL_SWEEP_THREADS, sweep_smem, st>>>(
+          ip, jp, jb, prm_atom, nip, njp, nsplit, box, a.box_mode, pc, coef, energy,
+          with_grad ? out : nullptr);
+      timer.end(st);
+      CVP_LAUNCH_CHECK();
+      return CVP_OK;
+    };
+    const double rc = d.cutoff;
+    const double exp_neg_beta = exp(-d.beta);
+    const int finish_blocks = (int)div_up(B * 32, 128);
+    int status;
+    if (KIND == CVP_PAIR_SOFTMIN) {
+      if ((status = sweep(true, false, nullptr, partials)) != CVP_OK) return status;
+      pair_finish_kernel<T, KIND><<<finish_blocks, 128, 0, st>>>(
+          partials, nsplit, nullptr, 1.0, rc, exp_neg_beta, value, frame_coef, accumulate ? 1 : 0, B);
+      CVP_LAUNCH_CHECK();
+      if (need_grad && (status = sweep(true, true, frame_coef, nullptr)) != CVP_OK) return status;
+    } else {
+      if ((status = sweep(true, need_grad, nullptr, partials)) != CVP_OK) return status;
+      pair_finish_kernel<T, KIND><<<finish_blocks, 128, 0, st>>>(
+          partials, nsplit, has_ex ? excluded : nullptr, d.scale, rc, exp_neg_beta, value, nullptr,
+          accumulate ? 1 : 0, B);
+      CVP_LAUNCH_CHECK();
+    }
+    if (!need_grad) return CVP_OK;
+    if ((status = sweep(false, true, frame_coef, nullptr)) != CVP_OK) return status;
+    if (!accumulate)
+      CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+    const T gscale = KIND == CVP_PAIR_SOFTMIN ? T(1) : (T)d.scale;
+    {
+      int64_t total = B * (int64_t)n1p;
+      int blocks = (int)std::min<int64_t>(div_up(total, 256), 148 * 16);
+      cell_scatter_kernel<T><<<blocks, 256, 0, st>>>(s1, gr1, n1p, N, gscale, grad, total);
+      CVP_LAUNCH_CHECK();
+      total = B * (int64_t)n2p;
+      blocks = (int)std::min<int64_t>(div_up(total, 256), 148 * 16);
+      cell_scatter_kernel<T><<<blocks, 256, 0, st>>>(s2, gr2, n2p, N, gscale, grad, total);
+      CVP_LAUNCH_CHECK();
+    }
+    if (has_ex) {
+      int64_t total = B * (int64_t)ex_atoms.size();
+      exclusion_gradient_kernel<T, KIND, PBC><<<(unsigned)div_up(total, 128), 128, 0, st>>>(
+          pos, N, prm_atom, static_cast<const int32_t*>(d_ex_atoms.ptr),
+          static_cast<const int32_t*>(d_ex_offsets.ptr),
+          static_cast<const int32_t*>(d_ex_partners.ptr), (int)ex_atoms.size(), box, a.box_mode,
+          pc, gscale, grad, total);
+      CVP_LAUNCH_CHECK();
+    }
+    return CVP_OK;
+  }
+
   template <typename T, int KIND, int PBC, bool OVERLAP>
   int run_impl(const EvalArgs& a, void* ws) {
+    if (cells_eligible(PBC)) return run_cells<T, KIND, PBC, OVERLAP>(a, ws);
     using T4 = typename Vec4<T>::type;
     constexpr int NCH = PairFn<T, KIND>::NCH;
     const int which = std::is_same<T, float>::value ? 0 : 1;
