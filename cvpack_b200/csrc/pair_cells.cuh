@@ -29,7 +29,7 @@ constexpr int CELL_SORT_THREADS = 512;
 constexpr int CELL_MAX_AXIS = 16;      // cells per axis (<= 4096 cells)
 constexpr int CELL_MAX_CELLS = CELL_MAX_AXIS * CELL_MAX_AXIS * CELL_MAX_AXIS;
 constexpr int CELL_SWEEP_THREADS = 512;
-constexpr int CELL_SMEM_BUDGET = 100 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
+constexpr int CELL_SMEM_BUDGET = 96 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
 constexpr int TAG_DUMMY = -1;
 
 __host__ __device__ inline int cell_round_up(int n, int m) { return (n + m - 1) / m * m; }
@@ -273,7 +273,7 @@ __host__ __device__ inline int cell_jchunk() {
 }
 
 // grid = B * nsplit CTAs; CTA (b, part) owns the i tiles part, part + nsplit, ... (strided by warp).
-template <typename T, int KIND, int PBC, bool OVERLAP, bool GRAD>
+template <typename T, int KIND, int PBC, bool OVERLAP, bool GRAD, bool FAST6>
 __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
     cell_sweep_kernel(const typename Vec4<T>::type* __restrict__ isorted,
                       const typename Vec4<T>::type* __restrict__ jsorted,
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   extern __shared__ __align__(128) unsigned char sweep_smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ double scratch[NCH * NWARP];
+  __shared__ __align__(16) T4 stage[NWARP][CELL_TILE];
 
   const int jchunk = cell_jchunk<T>();
   T4* jsm = reinterpret_cast<T4*>(sweep_smem);
@@ -388,33 +389,52 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         hi[c] = T(0.5) * (mx[c] - mn[c]);
       }
 
-      // ---- phase 2: every lane evaluates its own hits of the current batch of 4 clusters ----
+      // A *batch* = up to 4 surviving clusters, copied (already shifted to the right periodic
+      // image) into this warp's staging buffer.  Phase 1 tests all 32 staged atoms against the
+      // lane's i atom and records hits in a bitmask; phase 2 lets every lane walk its own hits.
       uint32_t hits = 0;
-      int nbatch = 0, bc0 = 0, bc1 = 0, bc2 = 0, bc3 = 0;
-      auto flush = [&]() {
+      int nbatch = 0;
+      bool batch_unsafe = false;
+      T4* stg = &stage[warp][0];
+      auto run_batch = [&]() {
+        __syncwarp();
+        for (int c = 0; c < nbatch; ++c) {
+          uint32_t m = 0;
+#pragma unroll
+          for (int u = 0; u < CELL_CLUSTER; ++u) {
+            const T4 pj = stg[c * CELL_CLUSTER + u];
+            T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+            if (batch_unsafe) pair_min_image<PBC>(dx, dy, dz, bx);
+            const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            m |= (r2 < pc.cutoff2 ? 1u : 0u) << u;
+          }
+          hits |= m << (c * CELL_CLUSTER);
+        }
         while (__any_sync(FULL, hits != 0u)) {
           if (hits != 0u) {
             const int k = __ffs(hits) - 1;
             hits &= hits - 1u;
-            const int slot = k >> 3;
-            const int cl = slot == 0 ? bc0 : (slot == 1 ? bc1 : (slot == 2 ? bc2 : bc3));
-            const T4 pj = jsm[cl * CELL_CLUSTER + (k & 7)];
+            const T4 pj = stg[k];
             const int tagj = tag_decode(pj.w);
             T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-            pair_min_image<PBC>(dx, dy, dz, bx);
-            const T r2 = dx * dx + dy * dy + dz * dz;
-            bool ok = r2 < pc.cutoff2 && tagj >= 0 && tagi >= 0;
+            if (batch_unsafe) pair_min_image<PBC>(dx, dy, dz, bx);
+            const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            bool ok = tagj >= 0 && tagi >= 0;
             T w = T(1);
             if (OVERLAP) {
               if (((tagi ^ tagj) & TAG_INDEX_MASK) == 0) ok = false;
               if (tagi & tagj & TAG_BOTH) w = T(0.5);
             }
             if (ok) {
-              T4 qj;
-              if (PRM) qj = atom_params[tagj & TAG_INDEX_MASK];
               T e[NCH];
               T coef;
-              Fn::eval(pc, r2, qi, qj, fc, e, coef);
+              if (FAST6) {
+                contacts_rational6(pc, r2, e[0], coef);
+              } else {
+                T4 qj;
+                if (PRM) qj = atom_params[tagj & TAG_INDEX_MASK];
+                Fn::eval(pc, r2, qi, qj, fc, e, coef);
+              }
 #pragma unroll
               for (int c = 0; c < NCH; ++c) en[c] += w * e[c];
               if (GRAD) {
@@ -426,7 +446,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             }
           }
         }
+        __syncwarp();
         nbatch = 0;
+        batch_unsafe = false;
       };
 
       for (int c0 = 0; c0 < ncl; c0 += 32) {
@@ -459,42 +481,21 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           const int src = __ffs(cmask) - 1;
           cmask &= cmask - 1u;
           const int cl = c0 + src;
-          const bool sf = __shfl_sync(FULL, (int)safe, src) != 0;
-          const int bit0 = nbatch * CELL_CLUSTER;
-          // ---- phase 1: distance test of the 8 atoms of the cluster ----
-          if (sf) {
-            const T xs = pi.x + __shfl_sync(FULL, sh[0], src);
-            const T ys = pi.y + __shfl_sync(FULL, sh[1], src);
-            const T zs = pi.z + __shfl_sync(FULL, sh[2], src);
-#pragma unroll
-            for (int k = 0; k < CELL_CLUSTER; ++k) {
-              const T4 pj = jsm[cl * CELL_CLUSTER + k];
-              const T dx = pj.x - xs, dy = pj.y - ys, dz = pj.z - zs;
-              const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-              if (r2 < pc.cutoff2) hits |= 1u << (bit0 + k);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < CELL_CLUSTER; ++k) {
-              const T4 pj = jsm[cl * CELL_CLUSTER + k];
-              T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-              min_image<PBC>(dx, dy, dz, bx);
-              const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-              if (r2 < pc.cutoff2) hits |= 1u << (bit0 + k);
-            }
+          const T shx = __shfl_sync(FULL, sh[0], src);
+          const T shy = __shfl_sync(FULL, sh[1], src);
+          const T shz = __shfl_sync(FULL, sh[2], src);
+          batch_unsafe |= __shfl_sync(FULL, (int)safe, src) == 0;
+          if ((lane >> 3) == nbatch) {
+            T4 pj = jsm[cl * CELL_CLUSTER + (lane & 7)];
+            pj.x -= shx;  // d = (x_j - shift) - x_i is the minimum image for a safe cluster
+            pj.y -= shy;
+            pj.z -= shz;
+            stg[lane] = pj;
           }
-          if (nbatch == 0)
-            bc0 = cl;
-          else if (nbatch == 1)
-            bc1 = cl;
-          else if (nbatch == 2)
-            bc2 = cl;
-          else
-            bc3 = cl;
-          if (++nbatch == 4) flush();
+          if (++nbatch == 4) run_batch();
         }
       }
-      flush();
+      if (nbatch > 0) run_batch();
       if (GRAD) {
         T4 g;
         g.x = gx;

@@ -14,6 +14,7 @@ struct PairConsts {
   T inv_range;  // 1/(rc - rs)
   int has_switch;
   T inv_r0;
+  T inv_r0sq;   // 1/r0^2
   StepParams step;
   T inv_rc;     // attraction: x = r/rc
   T ke;         // attraction: Coulomb constant
@@ -65,6 +66,44 @@ __device__ __forceinline__ void switching(const PairConsts<T>& pc, T r, T& e, T&
   }
 }
 
+// single-instruction reciprocal / reciprocal square root (MUFU); ~2 ulp, far inside the 1e-5 budget
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+
+// NumberOfContacts with the default step function 1/(1+x^6): everything but the switching needs
+// only r^2 (x^6 = (r^2/r0^2)^3); branch-free switching.
+template <typename T>
+__device__ __forceinline__ void contacts_rational6(const PairConsts<T>& pc, T r2, T& e, T& coef) {
+  const T inv_r = fast_rsqrt(r2);
+  const T x2 = r2 * pc.inv_r0sq;
+  const T x6 = x2 * x2 * x2;
+  const T s = fast_rcp(T(1) + x6);
+  const T inv_r2 = inv_r * inv_r;
+  T c = T(-6) * x6 * s * s * inv_r2;  // (dS/dr)/r
+  T en = s;
+  if (pc.has_switch) {
+    const T r = r2 * inv_r;
+    const T t = fmax((r - pc.rs) * pc.inv_range, T(0));
+    const T t2 = t * t;
+    const T sw = fma(t2 * t, fma(t, fma(T(-6), t, T(15)), T(-10)), T(1));
+    const T dsw = t2 * fma(t, fma(T(-30), t, T(60)), T(-30)) * pc.inv_range;
+    c = fma(c, sw, s * dsw * inv_r);
+    en = s * sw;
+  }
+  e = en;
+  coef = c;
+}
+
 // ---- pair functions: energy e and coef = (de/dr)/r for a pair at squared distance r2 -----------
 template <typename T, int KIND>
 struct PairFn;
@@ -76,7 +115,7 @@ struct PairFn<T, CVP_PAIR_CONTACTS> {
   static constexpr bool HAS_PARAMS = false;
   __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4&, const T4&,
                                               const T*, T (&e)[1], T& coef) {
-    T inv_r = rsqrt_t(r2);
+    T inv_r = fast_rsqrt(r2);
     T r = r2 * inv_r;
     T s, ds;
     step_function(pc.step, r * pc.inv_r0, s, ds);

@@ -443,6 +443,7 @@ struct PairSumCV : cvp_cv {
     pc.rs = sw ? (T)d.switch_distance : (T)0;
     pc.inv_range = sw ? (T)(1.0 / (d.cutoff - d.switch_distance)) : (T)0;
     pc.inv_r0 = d.r0 > 0 ? (T)(1.0 / d.r0) : (T)1;
+    pc.inv_r0sq = d.r0 > 0 ? (T)(1.0 / (d.r0 * d.r0)) : (T)1;
     pc.step.kind = d.step_kind;
     pc.step.n = (int)d.step_p0;
     pc.step.m = (int)d.step_p1;
@@ -520,8 +521,15 @@ struct PairSumCV : cvp_cv {
       const T4* jb = first ? bb2 : bb1;
       const int nip = first ? n1p : n2p, njp = first ? n2p : n1p;
       T4* out = first ? gr1 : gr2;
-      auto kernel = with_grad ? cell_sweep_kernel<T, KIND, CPBC, OVERLAP, true>
-                              : cell_sweep_kernel<T, KIND, CPBC, OVERLAP, false>;
+      // default step function 1/(1+x^6): specialised pair function
+      const bool fast6 = KIND == CVP_PAIR_CONTACTS && d.step_kind == CVP_STEP_RATIONAL &&
+                         (int)d.step_p0 == 6;
+      constexpr bool CAN_FAST6 = KIND == CVP_PAIR_CONTACTS;
+      auto kernel = with_grad ? cell_sweep_kernel<T, KIND, CPBC, OVERLAP, true, false>
+                              : cell_sweep_kernel<T, KIND, CPBC, OVERLAP, false, false>;
+      if (fast6)
+        kernel = with_grad ? cell_sweep_kernel<T, KIND, CPBC, OVERLAP, true, CAN_FAST6>
+                           : cell_sweep_kernel<T, KIND, CPBC, OVERLAP, false, CAN_FAST6>;
       CVP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sweep_smem));
       timer.begin("sweep", st);
@@ -954,6 +962,7 @@ struct CentroidPairSumCV : cvp_cv {
     pc.cutoff2 = (T)3.0e38;
     pc.has_switch = 0;
     pc.inv_r0 = (T)(1.0 / d.r0);
+    pc.inv_r0sq = (T)(1.0 / (d.r0 * d.r0));
     pc.step.kind = d.step_kind;
     pc.step.n = (int)d.step_p0;
     pc.step.m = (int)d.step_p1;
