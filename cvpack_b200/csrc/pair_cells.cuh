@@ -29,7 +29,8 @@ constexpr int CELL_SORT_THREADS = 512;
 constexpr int CELL_MAX_AXIS = 16;      // cells per axis (<= 4096 cells)
 constexpr int CELL_MAX_CELLS = CELL_MAX_AXIS * CELL_MAX_AXIS * CELL_MAX_AXIS;
 constexpr int CELL_SWEEP_THREADS = 512;
-constexpr int CELL_SMEM_BUDGET = 96 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
+constexpr int CELL_BATCH = 8;          // clusters per staged batch (64 atoms, one 64-bit hit mask)
+constexpr int CELL_SMEM_BUDGET = 88 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
 constexpr int TAG_DUMMY = -1;
 
 __host__ __device__ inline int cell_round_up(int n, int m) { return (n + m - 1) / m * m; }
@@ -122,17 +123,19 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
     }
     __syncthreads();
   }
-  // grid: cells of about CELL_CLUSTER atoms each, at most CELL_MAX_AXIS per axis
+  // two-level grid: coarse cells of about CELL_TILE atoms (so that 32 consecutive atoms, one warp's
+  // tile, form a compact blob rather than a rod), each split in 2x2x2 octants visited in Gray-code
+  // order (so that 8 consecutive atoms, one cluster, cover about two adjacent octants)
   const T volume = len[0] * len[1] * len[2];
-  const T edge = cbrt(volume * T(CELL_CLUSTER) / T(n));
+  const T edge = cbrt(volume * T(CELL_TILE) / T(n));
   int dims[3];
   T inv_cell[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    dims[c] = max(1, min(CELL_MAX_AXIS, (int)(len[c] / edge + T(0.5))));
+    dims[c] = max(1, min(CELL_MAX_AXIS / 2, (int)(len[c] / edge + T(0.5))));
     inv_cell[c] = T(dims[c]) / len[c];
   }
-  const int ncells = dims[0] * dims[1] * dims[2];
+  const int ncells = dims[0] * dims[1] * dims[2] * 8;
 
   for (int c = tid; c <= CELL_MAX_CELLS; c += CELL_SORT_THREADS) start[c] = 0;
   for (int c = tid; c < CELL_MAX_CELLS; c += CELL_SORT_THREADS) fill[c] = 0;
@@ -148,15 +151,20 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
     }
   };
   auto cell_index = [&](const T (&w)[3]) {
-    int cc[3];
+    int cc[3], octant = 0;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      cc[c] = max(0, min(dims[c] - 1, (int)((w[c] - lo[c]) * inv_cell[c])));
-    // serpentine order: consecutive cells are always spatial neighbours
+    for (int c = 0; c < 3; ++c) {
+      const T f = (w[c] - lo[c]) * inv_cell[c];
+      cc[c] = max(0, min(dims[c] - 1, (int)f));
+      if (f - T(cc[c]) >= T(0.5)) octant |= 1 << c;
+    }
+    // serpentine order: consecutive coarse cells are always spatial neighbours
     const int y = (cc[2] & 1) ? dims[1] - 1 - cc[1] : cc[1];
     const int row = cc[2] * dims[1] + y;
     const int x = (row & 1) ? dims[0] - 1 - cc[0] : cc[0];
-    return row * dims[0] + x;
+    // position of octant code (z<<2 | y<<1 | x) along the 3-bit Gray-code walk 0,1,3,2,6,7,5,4
+    const int gray_position = (0x54672310 >> (4 * octant)) & 7;
+    return (row * dims[0] + x) * 8 + gray_position;
   };
 
   // histogram
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   extern __shared__ __align__(128) unsigned char sweep_smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ double scratch[NCH * NWARP];
-  __shared__ __align__(16) T4 stage[NWARP][CELL_TILE];
+  __shared__ __align__(16) T4 stage[NWARP][CELL_BATCH * CELL_CLUSTER];
 
   const int jchunk = cell_jchunk<T>();
   T4* jsm = reinterpret_cast<T4*>(sweep_smem);
@@ -389,35 +397,60 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         hi[c] = T(0.5) * (mx[c] - mn[c]);
       }
 
-      // A *batch* = up to 4 surviving clusters, copied (already shifted to the right periodic
-      // image) into this warp's staging buffer.  Phase 1 tests all 32 staged atoms against the
-      // lane's i atom and records hits in a bitmask; phase 2 lets every lane walk its own hits.
-      uint32_t hits = 0;
+      // A *batch* = up to CELL_BATCH surviving clusters (64 atoms), copied -- already shifted to the
+      // right periodic image -- into this warp's staging buffer.  Phase 1 tests every staged atom
+      // against the lane's i atom and records hits in a 64-bit mask; phase 2 lets every lane walk
+      // its own hits, so the expensive pair function runs for real contacts only.  The larger the
+      // batch, the closer the busiest lane is to the average one.
+      uint32_t hits_lo = 0, hits_hi = 0;  // staged atoms 0..31 / 32..63
       int nbatch = 0;
       bool batch_unsafe = false;
       T4* stg = &stage[warp][0];
-      auto run_batch = [&]() {
-        __syncwarp();
-        for (int c = 0; c < nbatch; ++c) {
-          uint32_t m = 0;
+      auto run_phases = [&](auto unsafe_tag) {
+        constexpr bool UNSAFE = decltype(unsafe_tag)::value;
+        auto test = [&](int slot) -> bool {
+          const T4 pj = stg[slot];
+          T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+          if (UNSAFE) pair_min_image<PBC>(dx, dy, dz, bx);
+          return fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2;
+        };
+        if (nbatch == CELL_BATCH) {
+          // full batch: bit positions are compile-time constants
 #pragma unroll
-          for (int u = 0; u < CELL_CLUSTER; ++u) {
-            const T4 pj = stg[c * CELL_CLUSTER + u];
-            T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-            if (batch_unsafe) pair_min_image<PBC>(dx, dy, dz, bx);
-            const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            m |= (r2 < pc.cutoff2 ? 1u : 0u) << u;
+          for (int u = 0; u < 32; ++u) {
+            if (test(u)) hits_lo |= 1u << u;
           }
-          hits |= m << (c * CELL_CLUSTER);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            if (test(32 + u)) hits_hi |= 1u << u;
+          }
+        } else {
+          for (int c = 0; c < nbatch; ++c) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int u = 0; u < CELL_CLUSTER; ++u) {
+              if (test(c * CELL_CLUSTER + u)) m |= 1u << u;
+            }
+            if (c < 4)
+              hits_lo |= m << (c * CELL_CLUSTER);
+            else
+              hits_hi |= m << ((c - 4) * CELL_CLUSTER);
+          }
         }
-        while (__any_sync(FULL, hits != 0u)) {
-          if (hits != 0u) {
-            const int k = __ffs(hits) - 1;
-            hits &= hits - 1u;
+        while (__any_sync(FULL, (hits_lo | hits_hi) != 0u)) {
+          if ((hits_lo | hits_hi) != 0u) {
+            int k;
+            if (hits_lo != 0u) {
+              k = __ffs(hits_lo) - 1;
+              hits_lo &= hits_lo - 1u;
+            } else {
+              k = 31 + __ffs(hits_hi);
+              hits_hi &= hits_hi - 1u;
+            }
             const T4 pj = stg[k];
             const int tagj = tag_decode(pj.w);
             T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-            if (batch_unsafe) pair_min_image<PBC>(dx, dy, dz, bx);
+            if (UNSAFE) pair_min_image<PBC>(dx, dy, dz, bx);
             const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             bool ok = tagj >= 0 && tagi >= 0;
             T w = T(1);
@@ -446,6 +479,15 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             }
           }
         }
+      };
+      auto run_batch = [&]() {
+        __syncwarp();
+        // the per-pair minimum image is needed only when some (tile, cluster) pair of the batch is
+        // too wide for a single shift; a warp-uniform branch keeps it out of the common path
+        if (PBC == 1 && batch_unsafe)
+          run_phases(std::true_type{});
+        else
+          run_phases(std::false_type{});
         __syncwarp();
         nbatch = 0;
         batch_unsafe = false;
@@ -485,14 +527,14 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           const T shy = __shfl_sync(FULL, sh[1], src);
           const T shz = __shfl_sync(FULL, sh[2], src);
           batch_unsafe |= __shfl_sync(FULL, (int)safe, src) == 0;
-          if ((lane >> 3) == nbatch) {
-            T4 pj = jsm[cl * CELL_CLUSTER + (lane & 7)];
+          if (lane < CELL_CLUSTER) {
+            T4 pj = jsm[cl * CELL_CLUSTER + lane];
             pj.x -= shx;  // d = (x_j - shift) - x_i is the minimum image for a safe cluster
             pj.y -= shy;
             pj.z -= shz;
-            stg[lane] = pj;
+            stg[nbatch * CELL_CLUSTER + lane] = pj;
           }
-          if (++nbatch == 4) run_batch();
+          if (++nbatch == CELL_BATCH) run_batch();
         }
       }
       if (nbatch > 0) run_batch();

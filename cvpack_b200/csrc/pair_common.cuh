@@ -12,6 +12,7 @@ struct PairConsts {
   T cutoff2;    // squared cutoff (huge if none)
   T rs;         // switching distance
   T inv_range;  // 1/(rc - rs)
+  T neg30_inv_range;  // -30/(rc - rs)
   int has_switch;
   T inv_r0;
   T inv_r0sq;   // 1/r0^2
@@ -92,11 +93,12 @@ __device__ __forceinline__ void contacts_rational6(const PairConsts<T>& pc, T r2
   T c = T(-6) * x6 * s * s * inv_r2;  // (dS/dr)/r
   T en = s;
   if (pc.has_switch) {
+    // sw = 1 - t^3 (10 - 15 t + 6 t^2),  dsw/dr = -30 t^2 (1 - t)^2 / (rc - rs),  t clamped at 0
     const T r = r2 * inv_r;
     const T t = fmax((r - pc.rs) * pc.inv_range, T(0));
-    const T t2 = t * t;
-    const T sw = fma(t2 * t, fma(t, fma(T(-6), t, T(15)), T(-10)), T(1));
-    const T dsw = t2 * fma(t, fma(T(-30), t, T(60)), T(-30)) * pc.inv_range;
+    const T tu = t * (T(1) - t);
+    const T sw = fma(-(t * t * t), fma(t, fma(T(6), t, T(-15)), T(10)), T(1));
+    const T dsw = pc.neg30_inv_range * tu * tu;
     c = fma(c, sw, s * dsw * inv_r);
     en = s * sw;
   }

@@ -442,6 +442,7 @@ struct PairSumCV : cvp_cv {
     pc.has_switch = sw ? 1 : 0;
     pc.rs = sw ? (T)d.switch_distance : (T)0;
     pc.inv_range = sw ? (T)(1.0 / (d.cutoff - d.switch_distance)) : (T)0;
+    pc.neg30_inv_range = sw ? (T)(-30.0 / (d.cutoff - d.switch_distance)) : (T)0;
     pc.inv_r0 = d.r0 > 0 ? (T)(1.0 / d.r0) : (T)1;
     pc.inv_r0sq = d.r0 > 0 ? (T)(1.0 / (d.r0 * d.r0)) : (T)1;
     pc.step.kind = d.step_kind;
