@@ -200,7 +200,117 @@ __global__ void __launch_bounds__(GYR_THREADS)
   }
 }
 
+// ---- streaming fast path: contiguous, 16-byte aligned group, no periodic box, FP32 -------------------
+// 4 atoms (3 x float4) per thread iteration; weights read only for a mass-weighted centre.
+constexpr int GYR_FAST_SLICE = 4096;
+
+__device__ __forceinline__ void gyr_unpack4(const float4& a0, const float4& a1, const float4& a2,
+                                            float (&x)[4], float (&y)[4], float (&z)[4]) {
+  x[0] = a0.x; y[0] = a0.y; z[0] = a0.z;
+  x[1] = a0.w; y[1] = a1.x; z[1] = a1.y;
+  x[2] = a1.z; y[2] = a1.w; z[2] = a2.x;
+  x[3] = a2.y; y[3] = a2.z; z[3] = a2.w;
+}
+
+__global__ void __launch_bounds__(GYR_THREADS)
+    gyration_sums_fast_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom, int n,
+                              const float* __restrict__ weights, int nslice,
+                              double* __restrict__ partials) {
+  __shared__ double scratch[7 * (GYR_THREADS / 32)];
+  const int64_t b = blockIdx.x / nslice;
+  const int s = blockIdx.x - (int)b * nslice;
+  const float4* px = reinterpret_cast<const float4*>(pos + (b * num_atoms + first_atom) * 3);
+  const float4* pw = reinterpret_cast<const float4*>(weights);
+  const int g_begin = s * (GYR_FAST_SLICE / 4);
+  const int g_end = min(n / 4, g_begin + GYR_FAST_SLICE / 4);
+  const double uniform = 1.0 / n;
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int g = g_begin + threadIdx.x; g < g_end; g += GYR_THREADS) {
+    const float4 a0 = __ldg(px + 3 * g), a1 = __ldg(px + 3 * g + 1), a2 = __ldg(px + 3 * g + 2);
+    float x[4], y[4], z[4];
+    gyr_unpack4(a0, a1, a2, x, y, z);
+    float w[4];
+    if (weights != nullptr) {
+      const float4 wv = __ldg(pw + g);
+      w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double xd = x[k], yd = y[k], zd = z[k];
+      if (weights != nullptr) {
+        v[0] += (double)w[k] * xd;
+        v[1] += (double)w[k] * yd;
+        v[2] += (double)w[k] * zd;
+      }
+      v[3] += xd;
+      v[4] += yd;
+      v[5] += zd;
+      v[6] += xd * xd + yd * yd + zd * zd;
+    }
+  }
+  if (weights == nullptr) {
+    v[0] = v[3] * uniform;
+    v[1] = v[4] * uniform;
+    v[2] = v[5] * uniform;
+  }
+  block_sum<7>(v, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) partials[((size_t)b * nslice + s) * 7 + k] = v[k];
+  }
+}
+
+__global__ void __launch_bounds__(GYR_THREADS)
+    gyration_gradient_fast_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom,
+                                  int n, const float* __restrict__ weights, int nslice,
+                                  const GyrationFrame* __restrict__ rec, float* __restrict__ grad,
+                                  int accumulate) {
+  const int64_t b = blockIdx.x / nslice;
+  const int s = blockIdx.x - (int)b * nslice;
+  const float4* px = reinterpret_cast<const float4*>(pos + (b * num_atoms + first_atom) * 3);
+  const float4* pw = reinterpret_cast<const float4*>(weights);
+  float4* pg = reinterpret_cast<float4*>(grad + (b * num_atoms + first_atom) * 3);
+  const int g_begin = s * (GYR_FAST_SLICE / 4);
+  const int g_end = min(n / 4, g_begin + GYR_FAST_SLICE / 4);
+  const GyrationFrame r = rec[b];
+  const float f = (float)r.factor;
+  const float c[3] = {(float)r.c[0], (float)r.c[1], (float)r.c[2]};
+  const float sw[3] = {(float)r.s[0], (float)r.s[1], (float)r.s[2]};
+  const float uniform = 1.0f / n;
+  for (int g = g_begin + threadIdx.x; g < g_end; g += GYR_THREADS) {
+    const float4 a0 = __ldg(px + 3 * g), a1 = __ldg(px + 3 * g + 1), a2 = __ldg(px + 3 * g + 2);
+    float x[4], y[4], z[4], w[4] = {uniform, uniform, uniform, uniform};
+    gyr_unpack4(a0, a1, a2, x, y, z);
+    if (weights != nullptr) {
+      const float4 wv = __ldg(pw + g);
+      w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
+    }
+    float gx[4], gy[4], gz[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gx[k] = f * ((x[k] - c[0]) - w[k] * sw[0]);
+      gy[k] = f * ((y[k] - c[1]) - w[k] * sw[1]);
+      gz[k] = f * ((z[k] - c[2]) - w[k] * sw[2]);
+    }
+    float4 o0 = make_float4(gx[0], gy[0], gz[0], gx[1]);
+    float4 o1 = make_float4(gy[1], gz[1], gx[2], gy[2]);
+    float4 o2 = make_float4(gz[2], gx[3], gy[3], gz[3]);
+    if (accumulate) {
+      const float4 p0 = pg[3 * g], p1 = pg[3 * g + 1], p2 = pg[3 * g + 2];
+      o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+      o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+      o2.x += p2.x; o2.y += p2.y; o2.z += p2.z; o2.w += p2.w;
+    }
+    __stcs(pg + 3 * g, o0);
+    __stcs(pg + 3 * g + 1, o1);
+    __stcs(pg + 3 * g + 2, o2);
+  }
+}
+
 struct GyrationCV : cvp_cv {
+  bool uniform_weights = false;
+  std::vector<float> weights_f32;
+  DeviceBuffer d_weights_f32;
   std::vector<int32_t> group;
   std::vector<double> weights;
   int periodic = 0, squared = 0;
@@ -209,10 +319,12 @@ struct GyrationCV : cvp_cv {
   ~GyrationCV() override {
     d_group.release();
     d_weights.release();
+    d_weights_f32.release();
   }
   int upload() override {
     int status = cvp::upload(d_group, group);
     if (status != CVP_OK) return status;
+    if ((status = cvp::upload(d_weights_f32, weights_f32)) != CVP_OK) return status;
     return cvp::upload(d_weights, weights);
   }
   int nslice() const { return (int)div_up((int64_t)group.size(), GYR_ATOMS_PER_BLOCK); }
@@ -245,10 +357,20 @@ struct GyrationCV : cvp_cv {
     const int warp_blocks = (int)div_up(B * 32, 128);
 
     timer.begin("gyration_sums", st);
-    gyration_sums_kernel<T><<<grid, GYR_THREADS, 0, st>>>(pos, N, idx, w, n, first, ns, partials);
+    // streaming fast path: FP32, no box, contiguous group starting on a 16-byte boundary
+    const bool use_fast = PBC == 0 && std::is_same<T, float>::value && contiguous && n % 4 == 0 &&
+                          first % 4 == 0 && N % 4 == 0;
+    const int fast_ns = (int)div_up(n, GYR_FAST_SLICE);
+    const float* wf = uniform_weights ? nullptr : static_cast<const float*>(d_weights_f32.ptr);
+    if (use_fast)
+      gyration_sums_fast_kernel<<<(unsigned)(B * fast_ns), GYR_THREADS, 0, st>>>(
+          reinterpret_cast<const float*>(pos), N, first, n, wf, fast_ns, partials);
+    else
+      gyration_sums_kernel<T><<<grid, GYR_THREADS, 0, st>>>(pos, N, idx, w, n, first, ns, partials);
     timer.end(st);
     CVP_LAUNCH_CHECK();
-    gyration_centre_kernel<T><<<warp_blocks, 128, 0, st>>>(partials, ns, n, PBC != 0, squared, rec,
+    const int ns_used = use_fast ? fast_ns : ns;
+    gyration_centre_kernel<T><<<warp_blocks, 128, 0, st>>>(partials, ns_used, n, PBC != 0, squared, rec,
                                                             value, accumulate ? 1 : 0, B);
     CVP_LAUNCH_CHECK();
     if (PBC != 0) {
@@ -264,8 +386,13 @@ struct GyrationCV : cvp_cv {
     if (!accumulate && !dense)
       CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
     timer.begin("gyration_gradient", st);
-    gyration_gradient_kernel<T, PBC><<<grid, GYR_THREADS, 0, st>>>(
-        pos, N, idx, w, n, first, ns, box, a.box_mode, rec, grad, accumulate ? 1 : 0);
+    if (use_fast)
+      gyration_gradient_fast_kernel<<<(unsigned)(B * fast_ns), GYR_THREADS, 0, st>>>(
+          reinterpret_cast<const float*>(pos), N, first, n, wf, fast_ns, rec,
+          reinterpret_cast<float*>(grad), accumulate ? 1 : 0);
+    else
+      gyration_gradient_kernel<T, PBC><<<grid, GYR_THREADS, 0, st>>>(
+          pos, N, idx, w, n, first, ns, box, a.box_mode, rec, grad, accumulate ? 1 : 0);
     timer.end(st);
     CVP_LAUNCH_CHECK();
     return CVP_OK;
@@ -308,6 +435,10 @@ int gyration_create(const cvp_gyration_desc* desc, cvp_cv** out) {
     if (a != cv->group[0] + i) contiguous = false;
   }
   cv->contiguous = contiguous;
+  cv->uniform_weights = true;
+  for (int i = 0; i < desc->n; ++i)
+    if (cv->weights[i] != cv->weights[0]) cv->uniform_weights = false;
+  cv->weights_f32.assign(cv->weights.begin(), cv->weights.end());
   cv->active_atoms = cv->group;
   std::sort(cv->active_atoms.begin(), cv->active_atoms.end());
   *out = cv;

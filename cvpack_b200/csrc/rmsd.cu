@@ -76,6 +76,64 @@ __global__ void __launch_bounds__(RMSD_WARPS * 32)
   }
 }
 
+// ---- streaming fast path: one group = a contiguous, 16-byte aligned run of atoms (FP32) ----------
+// The common large case (RMSD of a whole protein, BASELINE config 3) needs no index gather: the
+// frame slice is read as float4 (4 atoms = 3 x float4), the centred reference as float4 from L2.
+constexpr int RMSD_FAST_THREADS = 256;
+constexpr int RMSD_FAST_SLICE = 4096;  // atoms per block
+
+__device__ __forceinline__ void unpack4(const float4& a0, const float4& a1, const float4& a2,
+                                        float (&x)[4], float (&y)[4], float (&z)[4]) {
+  x[0] = a0.x; y[0] = a0.y; z[0] = a0.z;
+  x[1] = a0.w; y[1] = a1.x; z[1] = a1.y;
+  x[2] = a1.z; y[2] = a1.w; z[2] = a2.x;
+  x[3] = a2.y; y[3] = a2.z; z[3] = a2.w;
+}
+
+__global__ void __launch_bounds__(RMSD_FAST_THREADS)
+    rmsd_sums_fast_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom, int n,
+                          const float* __restrict__ ref, int nslice, double* __restrict__ partials) {
+  __shared__ double scratch[13 * (RMSD_FAST_THREADS / 32)];
+  const int64_t b = blockIdx.x / nslice;
+  const int s = blockIdx.x - (int)b * nslice;
+  const float4* px = reinterpret_cast<const float4*>(pos + (b * num_atoms + first_atom) * 3);
+  const float4* py = reinterpret_cast<const float4*>(ref);
+  const int g_begin = s * (RMSD_FAST_SLICE / 4);
+  const int g_end = min(n / 4, g_begin + RMSD_FAST_SLICE / 4);
+  double v[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) v[k] = 0.0;
+  for (int g = g_begin + threadIdx.x; g < g_end; g += RMSD_FAST_THREADS) {
+    const float4 a0 = __ldg(px + 3 * g), a1 = __ldg(px + 3 * g + 1), a2 = __ldg(px + 3 * g + 2);
+    const float4 r0 = __ldg(py + 3 * g), r1 = __ldg(py + 3 * g + 1), r2 = __ldg(py + 3 * g + 2);
+    float x[4], y[4], z[4], rx[4], ry[4], rz[4];
+    unpack4(a0, a1, a2, x, y, z);
+    unpack4(r0, r1, r2, rx, ry, rz);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double xd = x[k], yd = y[k], zd = z[k], rxd = rx[k], ryd = ry[k], rzd = rz[k];
+      v[0] += xd;
+      v[1] += yd;
+      v[2] += zd;
+      v[3] += xd * xd + yd * yd + zd * zd;
+      v[4] += xd * rxd;
+      v[5] += xd * ryd;
+      v[6] += xd * rzd;
+      v[7] += yd * rxd;
+      v[8] += yd * ryd;
+      v[9] += yd * rzd;
+      v[10] += zd * rxd;
+      v[11] += zd * ryd;
+      v[12] += zd * rzd;
+    }
+  }
+  block_sum<13>(v, scratch);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 13; ++k) partials[((size_t)b * nslice + s) * 13 + k] = v[k];
+  }
+}
+
 // ---- solve -------------------------------------------------------------------------------------
 // Largest eigenpair of a symmetric 4x4 matrix by cyclic Jacobi rotations (double precision; plays
 // the role of the JAMA eigen-decomposition in OpenMM's reference RMSD kernel).
@@ -299,7 +357,62 @@ __global__ void rmsd_gradient_kernel(const T* __restrict__ pos, int64_t num_atom
   }
 }
 
+// gradient of the streaming fast path: g = factor * (x - c - U^T y), 4 atoms per thread iteration
+__global__ void __launch_bounds__(RMSD_FAST_THREADS)
+    rmsd_gradient_fast_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom,
+                              int n, const float* __restrict__ ref,
+                              const RmsdSolution* __restrict__ solution,
+                              const double* __restrict__ seg_centroid,
+                              const double* __restrict__ group_factor, int nslice,
+                              float* __restrict__ grad, int accumulate) {
+  const int64_t b = blockIdx.x / nslice;
+  const int s = blockIdx.x - (int)b * nslice;
+  const float4* px = reinterpret_cast<const float4*>(pos + (b * num_atoms + first_atom) * 3);
+  const float4* py = reinterpret_cast<const float4*>(ref);
+  float4* pg = reinterpret_cast<float4*>(grad + (b * num_atoms + first_atom) * 3);
+  const int g_begin = s * (RMSD_FAST_SLICE / 4);
+  const int g_end = min(n / 4, g_begin + RMSD_FAST_SLICE / 4);
+  const float f = (float)group_factor[b];
+  float ut[9], c[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) ut[k] = (float)solution[b].ut[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c[k] = (float)seg_centroid[3 * b + k];
+  for (int g = g_begin + threadIdx.x; g < g_end; g += RMSD_FAST_THREADS) {
+    const float4 a0 = __ldg(px + 3 * g), a1 = __ldg(px + 3 * g + 1), a2 = __ldg(px + 3 * g + 2);
+    const float4 r0 = __ldg(py + 3 * g), r1 = __ldg(py + 3 * g + 1), r2 = __ldg(py + 3 * g + 2);
+    float x[4], y[4], z[4], rx[4], ry[4], rz[4], gx[4], gy[4], gz[4];
+    unpack4(a0, a1, a2, x, y, z);
+    unpack4(r0, r1, r2, rx, ry, rz);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gx[k] = f * ((x[k] - c[0]) - (ut[0] * rx[k] + ut[1] * ry[k] + ut[2] * rz[k]));
+      gy[k] = f * ((y[k] - c[1]) - (ut[3] * rx[k] + ut[4] * ry[k] + ut[5] * rz[k]));
+      gz[k] = f * ((z[k] - c[2]) - (ut[6] * rx[k] + ut[7] * ry[k] + ut[8] * rz[k]));
+    }
+    float4 o0 = make_float4(gx[0], gy[0], gz[0], gx[1]);
+    float4 o1 = make_float4(gy[1], gz[1], gx[2], gy[2]);
+    float4 o2 = make_float4(gz[2], gx[3], gy[3], gz[3]);
+    if (accumulate) {
+      const float4 p0 = pg[3 * g], p1 = pg[3 * g + 1], p2 = pg[3 * g + 2];
+      o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+      o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+      o2.x += p2.x; o2.y += p2.y; o2.z += p2.z; o2.w += p2.w;
+    }
+    __stcs(pg + 3 * g, o0);
+    __stcs(pg + 3 * g + 1, o1);
+    __stcs(pg + 3 * g + 2, o2);
+  }
+}
+
 struct RmsdCV : cvp_cv {
+  // streaming fast path (see rmsd_sums_fast_kernel)
+  bool fast = false;
+  int fast_first = 0, fast_nslice = 0;
+  std::vector<float> ref_f32;
+  std::vector<int32_t> fast_seg_slice_offsets;
+  std::vector<double> fast_gy;
+  DeviceBuffer d_ref_f32, d_fast_seg_slice_offsets, d_fast_gy;
   int num_groups = 0, nseg = 0, nslice = 0;
   int64_t num_entries = 0;
   CombineParams cp{};
@@ -318,7 +431,7 @@ struct RmsdCV : cvp_cv {
     for (DeviceBuffer* buf :
          {&d_entry_atom, &d_entry_group, &d_entry_seg, &d_ref, &d_slices, &d_group_seg_offsets,
           &d_seg_slice_offsets, &d_seg_size, &d_group_size, &d_group_gy, &d_active,
-          &d_atom_entry_offsets, &d_atom_entries})
+          &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_fast_seg_slice_offsets, &d_fast_gy})
       buf->release();
   }
   int upload() override {
@@ -338,11 +451,14 @@ struct RmsdCV : cvp_cv {
     CVP_UP(d_active, active_atoms);
     CVP_UP(d_atom_entry_offsets, atom_entry_offsets);
     CVP_UP(d_atom_entries, atom_entries);
+    CVP_UP(d_ref_f32, ref_f32);
+    CVP_UP(d_fast_seg_slice_offsets, fast_seg_slice_offsets);
+    CVP_UP(d_fast_gy, fast_gy);
 #undef CVP_UP
     return CVP_OK;
   }
   size_t workspace_per_frame(int, bool) const override {
-    return (size_t)nslice * 13 * sizeof(double) + (size_t)num_groups * sizeof(RmsdSolution) +
+    return (size_t)std::max(nslice, fast_nslice) * 13 * sizeof(double) + (size_t)num_groups * sizeof(RmsdSolution) +
            (size_t)nseg * 3 * sizeof(double) + (size_t)num_groups * sizeof(double) + 64;
   }
   size_t workspace_fixed(int) const override { return 6 * 256; }
@@ -365,7 +481,17 @@ struct RmsdCV : cvp_cv {
     double* seg_centroid = carve.take<double>((size_t)B * nseg * 3);
     double* group_factor = carve.take<double>((size_t)B * num_groups);
 
-    {
+    // streaming fast path: FP32, one contiguous aligned group
+    const bool use_fast = fast && std::is_same<T, float>::value && (N % 4) == 0;
+    const int ns = use_fast ? fast_nslice : nslice;
+    if (use_fast) {
+      timer.begin("rmsd_sums", st);
+      rmsd_sums_fast_kernel<<<(unsigned)(B * ns), RMSD_FAST_THREADS, 0, st>>>(
+          reinterpret_cast<const float*>(pos), N, fast_first, (int)num_entries,
+          static_cast<const float*>(d_ref_f32.ptr), ns, partials);
+      timer.end(st);
+      CVP_LAUNCH_CHECK();
+    } else {
       int64_t warps = B * nslice;
       timer.begin("rmsd_sums", st);
       rmsd_sums_kernel<T><<<(unsigned)div_up(warps, RMSD_WARPS), RMSD_WARPS * 32, 0, st>>>(
@@ -378,11 +504,13 @@ struct RmsdCV : cvp_cv {
     {
       int64_t total = B * num_groups;
       rmsd_solve_kernel<<<(unsigned)div_up(total, 64), 64, 0, st>>>(
-          partials, nslice, static_cast<const int32_t*>(d_group_seg_offsets.ptr),
-          static_cast<const int32_t*>(d_seg_slice_offsets.ptr),
+          partials, ns, static_cast<const int32_t*>(d_group_seg_offsets.ptr),
+          static_cast<const int32_t*>(use_fast ? d_fast_seg_slice_offsets.ptr
+                                               : d_seg_slice_offsets.ptr),
           static_cast<const int32_t*>(d_seg_size.ptr),
           static_cast<const int32_t*>(d_group_size.ptr),
-          static_cast<const double*>(d_group_gy.ptr), num_groups, B, solution, seg_centroid, nseg);
+          static_cast<const double*>(use_fast ? d_fast_gy.ptr : d_group_gy.ptr), num_groups, B,
+          solution, seg_centroid, nseg);
       CVP_LAUNCH_CHECK();
     }
     rmsd_combine_kernel<T><<<(unsigned)div_up(B, 128), 128, 0, st>>>(
@@ -392,6 +520,16 @@ struct RmsdCV : cvp_cv {
     if (grad == nullptr) return CVP_OK;
     if (!accumulate && !dense)
       CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+    if (use_fast) {
+      timer.begin("rmsd_gradient", st);
+      rmsd_gradient_fast_kernel<<<(unsigned)(B * ns), RMSD_FAST_THREADS, 0, st>>>(
+          reinterpret_cast<const float*>(pos), N, fast_first, (int)num_entries,
+          static_cast<const float*>(d_ref_f32.ptr), solution, seg_centroid, group_factor, ns,
+          reinterpret_cast<float*>(grad), accumulate ? 1 : 0);
+      timer.end(st);
+      CVP_LAUNCH_CHECK();
+      return CVP_OK;
+    }
     {
       const int num_active = (int)active_atoms.size();
       int64_t total = B * (int64_t)num_active;
@@ -517,6 +655,26 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
       cv->atom_entry_offsets.push_back((int32_t)cv->atom_entries.size());
     }
     cv->dense = (int)cv->active_atoms.size() == desc->num_atoms;
+  }
+  // streaming fast path: a single group/segment whose entries are atoms first, first+1, ... with a
+  // multiple-of-4 count and a 16-byte aligned start within the frame
+  if (G == 1 && cv->nseg == 1 && E % 4 == 0) {
+    bool contiguous = true;
+    for (int64_t e = 0; e < E && contiguous; ++e)
+      contiguous = cv->entry_atom[e] == cv->entry_atom[0] + (int32_t)e;
+    if (contiguous && cv->entry_atom[0] % 4 == 0) {
+      cv->fast = true;
+      cv->fast_first = cv->entry_atom[0];
+      cv->fast_nslice = (int)div_up(E, RMSD_FAST_SLICE);
+      cv->ref_f32.resize((size_t)E * 3);
+      double gy = 0.0;
+      for (size_t k = 0; k < cv->ref_f32.size(); ++k) {
+        cv->ref_f32[k] = (float)cv->ref[k];
+        gy += (double)cv->ref_f32[k] * (double)cv->ref_f32[k];
+      }
+      cv->fast_gy.assign(1, gy);
+      cv->fast_seg_slice_offsets = {0, cv->fast_nslice};
+    }
   }
   *out = cv;
   return CVP_OK;

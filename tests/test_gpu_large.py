@@ -1,0 +1,167 @@
+"""
+GPU parity at sizes beyond what the NumPy oracle finishes quickly -- checked against the C oracle --
+and, at BASELINE.json's full sizes, through size-independent properties (translation / rotation
+invariance, permutation of frames, linearity of the pair sum in the groups, zero net gradient).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import cvpack_b200 as cvpack
+from oracle import c_oracle
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def lattice_frames(rng, num_frames, num_atoms, box):
+    m = int(np.ceil(num_atoms ** (1 / 3)))
+    grid = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    sites = (grid[rng.permutation(m**3)[:num_atoms]] + 0.5) * (box / m)
+    return sites[None] + 0.3 * (box / m) * rng.normal(size=(num_frames, num_atoms, 3))
+
+
+def unit_system(n):
+    system = cvpack.System()
+    for _ in range(n):
+        system.addParticle(1.0)
+    return system
+
+
+def plain_nonbonded(n, periodic=True):
+    nb = cvpack.NonbondedForce()
+    for _ in range(n):
+        nb.addParticle(0.0, 0.3, 0.0)
+    nb.setNonbondedMethod(nb.CutoffPeriodic if periodic else nb.CutoffNonPeriodic)
+    return nb
+
+
+@pytest.mark.parametrize("precision,tol", [("single", 1e-5), ("double", 1e-10)])
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("cells", [1, 0])
+def test_contacts_medium_vs_c_oracle(precision, tol, periodic, cells):
+    rng = np.random.default_rng(31)
+    n, box = 6000, 3.9
+    x = lattice_frames(rng, 6, n, box)
+    system = unit_system(n)
+    cv = cvpack.NumberOfContacts(range(0, 3200), range(2800, n), plain_nonbonded(n, periodic),
+                                 thresholdDistance=0.6)
+    cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, [box] * 3 if periodic else None, precision=precision)
+    ctx._native_cv(cv).set_option("cells", cells)  # pylint: disable=protected-access
+    value, grad = cv.getValueAndGradient(ctx)
+    stored = ctx.getPositions().double().cpu().numpy()
+    ref_value, ref_grad = c_oracle.contacts_batch(
+        stored, range(0, 3200), range(2800, n), (), np.diag([box] * 3) if periodic else None,
+        r0=0.6, rc=1.2, rs=0.9,
+    )
+    v = value._value.double().cpu().numpy()
+    g = grad.double().cpu().numpy()
+    assert np.abs(v - ref_value).max() <= tol * np.abs(ref_value).max()
+    assert np.abs(g - ref_grad).max() <= tol * np.abs(ref_grad).max()
+
+
+@pytest.mark.parametrize("precision,tol", [("single", 1e-5), ("double", 1e-10)])
+def test_rmsd_and_rg_medium_vs_c_oracle(precision, tol):
+    rng = np.random.default_rng(32)
+    n = 40000
+    reference = 3.0 * rng.normal(size=(n, 3))
+    from scipy.spatial.transform import Rotation
+
+    rot = Rotation.random(4, random_state=1).as_matrix()
+    x = np.einsum("bij,nj->bni", rot, reference) + 0.05 * rng.normal(size=(4, n, 3)) + 2.0
+    system = helpers.make_system(n, rng)
+    rmsd = cvpack.RMSD(reference, range(n), n)
+    rg = cvpack.RadiusOfGyration(range(n))
+    rg_mass = cvpack.RadiusOfGyrationSq(range(n), weighByMass=True)
+    part = cvpack.RMSD(reference, range(4000, 30000), n)  # contiguous, not starting at 0
+    for cv in (rmsd, rg, rg_mass, part):
+        cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, precision=precision)
+    stored = ctx.getPositions().double().cpu().numpy()
+    masses = system.getMasses()
+    cases = [
+        (rmsd, c_oracle.rmsd_batch(stored, np.arange(n), reference)),
+        (part, c_oracle.rmsd_batch(stored, np.arange(4000, 30000), reference[4000:30000])),
+        (rg, c_oracle.gyration_batch(stored, np.arange(n))),
+        (rg_mass, c_oracle.gyration_batch(stored, np.arange(n), masses / masses.sum(), squared=True)),
+    ]
+    for cv, (ref_value, ref_grad) in cases:
+        value, grad = cv.getValueAndGradient(ctx)
+        v = value._value.double().cpu().numpy()
+        g = grad.double().cpu().numpy()
+        assert np.abs(v - ref_value).max() <= tol * np.abs(ref_value).max(), cv.getName()
+        assert np.abs(g - ref_grad).max() <= tol * np.abs(ref_grad).max(), cv.getName()
+
+
+def test_contacts_full_size_properties():
+    """BASELINE config 2 shape (10k x 10k atoms, L = 5.844 nm), 8 frames."""
+    rng = np.random.default_rng(33)
+    n, box = 20000, 5.844
+    x = lattice_frames(rng, 8, n, box).astype(np.float32)
+    system = unit_system(n)
+    nb = plain_nonbonded(n)
+    whole = cvpack.NumberOfContacts(range(0, 10000), range(10000, n), nb, thresholdDistance=0.6)
+    half_a = cvpack.NumberOfContacts(range(0, 5000), range(10000, n), nb, thresholdDistance=0.6)
+    half_b = cvpack.NumberOfContacts(range(5000, 10000), range(10000, n), nb, thresholdDistance=0.6)
+    for cv in (whole, half_a, half_b):
+        cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, [box] * 3)
+    v, g = whole.getValueAndGradient(ctx)
+    va, ga = half_a.getValueAndGradient(ctx)
+    vb, gb = half_b.getValueAndGradient(ctx)
+    v, va, vb = (t._value.double() for t in (v, va, vb))
+    # linearity in the first group
+    assert torch.allclose(v, va + vb, rtol=2e-6)
+    assert (g - (ga + gb)).abs().max() <= 2e-5 * g.abs().max()
+    # a pair sum exerts no net force
+    assert g.double().sum(dim=1).abs().max() <= 1e-3 * g.abs().max()
+    # translating every atom by a lattice vector, or by anything under PBC, changes nothing
+    shifted = x + np.array([box, -2 * box, 0.37], dtype=np.float32)
+    ctx.setPositions(shifted)
+    v2 = whole.getValue(ctx)._value.double()
+    assert torch.allclose(v, v2, rtol=2e-5)
+    # frames are independent: reversing the batch reverses the results, bit for bit
+    ctx.setPositions(x[::-1].copy())
+    v3, g3 = whole.getValueAndGradient(ctx)
+    assert torch.equal(v3._value.flip(0).double(), v)
+    assert torch.equal(g3.flip(0), g)
+    # all-pairs and cell-sorted paths agree
+    ctx.setPositions(x)
+    ctx._native_cv(whole).set_option("cells", 0)  # pylint: disable=protected-access
+    v4, g4 = whole.getValueAndGradient(ctx)
+    assert torch.allclose(v4._value.double(), v, rtol=2e-6)
+    assert (g4 - g).abs().max() <= 1e-5 * g.abs().max()
+
+
+def test_rmsd_full_size_properties():
+    """BASELINE config 3 shape (100k atoms), 6 frames: rigid motions give RMSD 0, noise gives sigma*sqrt(3)."""
+    rng = np.random.default_rng(34)
+    n = 100000
+    reference = (3.0 * rng.normal(size=(n, 3))).astype(np.float32)
+    from scipy.spatial.transform import Rotation
+
+    rot = Rotation.random(6, random_state=2).as_matrix()
+    sigma = 0.05
+    noise = sigma * rng.normal(size=(6, n, 3))
+    noise[0] = 0.0  # frame 0: pure rigid motion
+    x = np.einsum("bij,bnj->bni", rot, reference[None] + noise) + rng.normal(size=(6, 1, 3))
+    system = unit_system(n)
+    rmsd = cvpack.RMSD(reference.astype(np.float64), range(n), n)
+    rg = cvpack.RadiusOfGyration(range(n))
+    for cv in (rmsd, rg):
+        cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x)
+    value, grad = rmsd.getValueAndGradient(ctx)
+    v = value._value.double().cpu().numpy()
+    assert v[0] < 2e-3  # FP32 coordinates of a rotated structure: ~1e-7 nm * sqrt terms
+    expected = np.sqrt((noise[1:] ** 2).sum(axis=(1, 2)) / n)
+    assert np.allclose(v[1:], expected, rtol=2e-3)  # optimal alignment removes a tiny part of the noise
+    # |grad|^2 summed over atoms = 1/n for an RMSD
+    norm = (grad[1:].double() ** 2).sum(dim=(1, 2)).cpu().numpy()
+    assert np.allclose(norm, 1.0 / n, rtol=1e-4)
+    rgv = rg.getValue(ctx)._value.double().cpu().numpy()
+    stored = ctx.getPositions().double().cpu().numpy()
+    ref_rg, _ = c_oracle.gyration_batch(stored, np.arange(n), need_grad=False)
+    assert np.allclose(rgv, ref_rg, rtol=1e-6)
