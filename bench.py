@@ -43,7 +43,7 @@ WORKLOADS = {
     "contacts": dict(
         name="NumberOfContacts 10k x 10k atoms, cubic PBC L=5.844 nm, r0=0.6 rc=1.2 rs=0.9 nm, "
         "4096 frames/GPU of water density (100 atoms/nm^3)",
-        frames=4096, atoms=20000, box=5.844, r0=0.6, cpu_sample_frames=16,
+        frames=4096, atoms=20000, box=5.844, r0=0.6, cpu_sample_frames=32,
     ),
     # configs[2]
     "rmsd": dict(
@@ -229,6 +229,7 @@ def run_reference(args, spec: dict) -> None:
         return
     from oracle import c_oracle
 
+    c_oracle.use_all_threads()
     sample = spec["cpu_sample_frames"]
     x, reference = make_positions(args.workload, spec, sample, seed=1234)
     x = x.numpy()
@@ -407,6 +408,7 @@ def run_ours(args, spec: dict) -> None:
     if world == 1 and not args.no_cpu_baseline:
         from oracle import c_oracle
 
+        c_oracle.use_all_threads()
         sample = spec["cpu_sample_frames"]
         xs, ref = make_positions(args.workload, spec, sample, seed=1234)
         seconds = cpu_oracle_run(args.workload, spec, xs.numpy(), ref.numpy())

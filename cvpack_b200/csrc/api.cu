@@ -1,5 +1,7 @@
 // extern "C" entry points of libcvpack_b200.so (see include/cvpack_b200.h).
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -150,80 +152,82 @@ int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* 
   // chunk: at most ~256 MiB of coordinates, at least 1 frame, and >= 4 chunks when possible
   int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t(256) << 20) / frame_bytes));
   chunk = std::min(chunk, std::max<int64_t>(1, (num_frames + 3) / 4));
-  constexpr int SLOTS = 2;
-  struct Slot {
-    void *pos = nullptr, *grad = nullptr, *value = nullptr, *box = nullptr;
-    cudaStream_t stream = nullptr;
-  } slot[SLOTS];
-  void* shared_box = nullptr;
-  auto cleanup = [&]() {
-    for (auto& s : slot) {
-      if (s.stream) cudaStreamSynchronize(s.stream);
-      cudaFree(s.pos);
-      cudaFree(s.grad);
-      cudaFree(s.value);
-      cudaFree(s.box);
-      if (s.stream) cudaStreamDestroy(s.stream);
-    }
-    cudaFree(shared_box);
+  constexpr int SLOTS = HostPipeline::SLOTS;
+  HostPipeline& hp = cv->host;
+  const bool trace = std::getenv("CVP_HOST_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(now() - t0).count();
+  };
+  const auto t_start = now();
+  const bool have_box = box != nullptr && box_mode != CVP_BOX_NONE;
+  if ((status = hp.ensure()) != CVP_OK) return status;
+  if (have_box && box_mode == CVP_BOX_SHARED) {
+    if ((status = hp.shared_box.reserve(9 * es)) != CVP_OK) return status;
+    CVP_CUDA_CHECK(cudaMemcpy(hp.shared_box.ptr, box, 9 * es, cudaMemcpyHostToDevice));
+  }
+  for (int k = 0; k < SLOTS; ++k) {
+    if ((status = hp.pos[k].reserve((size_t)chunk * frame_bytes)) != CVP_OK) return status;
+    if (need_grad && (status = hp.grad[k].reserve((size_t)chunk * frame_bytes)) != CVP_OK)
+      return status;
+    if ((status = hp.value[k].reserve((size_t)chunk * es)) != CVP_OK) return status;
+    if (have_box && box_mode == CVP_BOX_PER_FRAME &&
+        (status = hp.box[k].reserve((size_t)chunk * 9 * es)) != CVP_OK)
+      return status;
+  }
+  // the spec's workspace is shared by both slots: kernels of consecutive chunks are serialised by
+  // an event chain, copies are not
+  const double setup_ms = ms_since(t_start);
+  const auto t_loop = now();
+  auto drain = [&]() {
+    for (int k = 0; k < SLOTS; ++k) cudaStreamSynchronize(hp.stream[k]);
   };
 #define CVP_HOST_CHECK(expr)                                                             \
   do {                                                                                   \
     cudaError_t e__ = (expr);                                                            \
     if (e__ != cudaSuccess) {                                                            \
       set_error(std::string(#expr) + " failed: " + cudaGetErrorString(e__));             \
-      cleanup();                                                                         \
+      drain();                                                                           \
       return CVP_ERR_CUDA;                                                               \
     }                                                                                    \
   } while (0)
-  const bool have_box = box != nullptr && box_mode != CVP_BOX_NONE;
-  if (have_box && box_mode == CVP_BOX_SHARED) {
-    CVP_HOST_CHECK(cudaMalloc(&shared_box, 9 * es));
-    CVP_HOST_CHECK(cudaMemcpy(shared_box, box, 9 * es, cudaMemcpyHostToDevice));
-  }
-  for (auto& s : slot) {
-    CVP_HOST_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CVP_HOST_CHECK(cudaMalloc(&s.pos, (size_t)chunk * frame_bytes));
-    if (need_grad) CVP_HOST_CHECK(cudaMalloc(&s.grad, (size_t)chunk * frame_bytes));
-    CVP_HOST_CHECK(cudaMalloc(&s.value, (size_t)chunk * es));
-    if (have_box && box_mode == CVP_BOX_PER_FRAME)
-      CVP_HOST_CHECK(cudaMalloc(&s.box, (size_t)chunk * 9 * es));
-  }
-  // the spec's workspace is shared by both slots: kernels of consecutive chunks are serialised by
-  // an event chain, copies are not
-  cudaEvent_t kernels_done[SLOTS] = {nullptr, nullptr};
-  for (auto& e : kernels_done) CVP_HOST_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   int64_t index = 0;
   status = CVP_OK;
   for (int64_t first = 0; first < num_frames && status == CVP_OK; first += chunk, ++index) {
-    Slot& s = slot[index % SLOTS];
+    const int k = (int)(index % SLOTS);
+    cudaStream_t stream = hp.stream[k];
     const int64_t count = std::min(chunk, num_frames - first);
-    CVP_HOST_CHECK(cudaMemcpyAsync(s.pos, static_cast<const char*>(positions) + (size_t)first * frame_bytes,
-                                   (size_t)count * frame_bytes, cudaMemcpyHostToDevice, s.stream));
-    const void* dbox = shared_box;
-    if (s.box) {
-      CVP_HOST_CHECK(cudaMemcpyAsync(s.box, static_cast<const char*>(box) + (size_t)first * 9 * es,
-                                     (size_t)count * 9 * es, cudaMemcpyHostToDevice, s.stream));
-      dbox = s.box;
+    CVP_HOST_CHECK(cudaMemcpyAsync(hp.pos[k].ptr,
+                                   static_cast<const char*>(positions) + (size_t)first * frame_bytes,
+                                   (size_t)count * frame_bytes, cudaMemcpyHostToDevice, stream));
+    const void* dbox = hp.shared_box.ptr;
+    if (have_box && box_mode == CVP_BOX_PER_FRAME) {
+      CVP_HOST_CHECK(cudaMemcpyAsync(hp.box[k].ptr,
+                                     static_cast<const char*>(box) + (size_t)first * 9 * es,
+                                     (size_t)count * 9 * es, cudaMemcpyHostToDevice, stream));
+      dbox = hp.box[k].ptr;
     }
     if (index > 0)
-      CVP_HOST_CHECK(cudaStreamWaitEvent(s.stream, kernels_done[(index - 1) % SLOTS], 0));
-    status = cvp_evaluate(cv, dtype, s.pos, dbox, have_box ? box_mode : CVP_BOX_NONE, count,
-                          num_atoms, s.value, s.grad, flags, s.stream);
+      CVP_HOST_CHECK(cudaStreamWaitEvent(stream, hp.kernels_done[(index - 1) % SLOTS], 0));
+    status = cvp_evaluate(cv, dtype, hp.pos[k].ptr, have_box ? dbox : nullptr,
+                          have_box ? box_mode : CVP_BOX_NONE, count, num_atoms, hp.value[k].ptr,
+                          need_grad ? hp.grad[k].ptr : nullptr, flags, stream);
     if (status != CVP_OK) break;
-    CVP_HOST_CHECK(cudaEventRecord(kernels_done[index % SLOTS], s.stream));
-    CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(value) + (size_t)first * es, s.value,
-                                   (size_t)count * es, cudaMemcpyDeviceToHost, s.stream));
+    CVP_HOST_CHECK(cudaEventRecord(hp.kernels_done[k], stream));
+    CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(value) + (size_t)first * es, hp.value[k].ptr,
+                                   (size_t)count * es, cudaMemcpyDeviceToHost, stream));
     if (need_grad)
-      CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(grad) + (size_t)first * frame_bytes, s.grad,
-                                     (size_t)count * frame_bytes, cudaMemcpyDeviceToHost, s.stream));
+      CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(grad) + (size_t)first * frame_bytes,
+                                     hp.grad[k].ptr, (size_t)count * frame_bytes,
+                                     cudaMemcpyDeviceToHost, stream));
   }
-  for (auto& s : slot)
-    if (s.stream) cudaStreamSynchronize(s.stream);
-  for (auto& e : kernels_done)
-    if (e) cudaEventDestroy(e);
+  drain();
   cudaError_t last = cudaGetLastError();
-  cleanup();
+  if (trace)
+    fprintf(stderr,
+            "[cvp_evaluate_host] device %d: setup %.1f ms, pipeline %.1f ms, %lld frames in chunks "
+            "of %lld\n",
+            device, setup_ms, ms_since(t_loop), (long long)num_frames, (long long)chunk);
   if (status == CVP_OK && last != cudaSuccess) {
     set_error(std::string("host evaluation failed: ") + cudaGetErrorString(last));
     return CVP_ERR_CUDA;

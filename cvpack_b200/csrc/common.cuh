@@ -157,15 +157,54 @@ struct KernelTimer {
 };
 }  // namespace cvp
 
+namespace cvp {
+// Device staging buffers, streams and events of the host-buffer path (cvp_evaluate_host); they live
+// as long as the spec so that repeated calls neither allocate nor free device memory.
+struct HostPipeline {
+  static constexpr int SLOTS = 2;
+  DeviceBuffer pos[SLOTS], grad[SLOTS], value[SLOTS], box[SLOTS], shared_box;
+  cudaStream_t stream[SLOTS] = {nullptr, nullptr};
+  cudaEvent_t kernels_done[SLOTS] = {nullptr, nullptr};
+  int ensure() {
+    for (int k = 0; k < SLOTS; ++k) {
+      if (!stream[k]) CVP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream[k], cudaStreamNonBlocking));
+      if (!kernels_done[k])
+        CVP_CUDA_CHECK(cudaEventCreateWithFlags(&kernels_done[k], cudaEventDisableTiming));
+    }
+    return CVP_OK;
+  }
+  void release() {
+    for (int k = 0; k < SLOTS; ++k) {
+      if (stream[k]) {
+        cudaStreamSynchronize(stream[k]);
+        cudaStreamDestroy(stream[k]);
+        stream[k] = nullptr;
+      }
+      if (kernels_done[k]) {
+        cudaEventDestroy(kernels_done[k]);
+        kernels_done[k] = nullptr;
+      }
+      pos[k].release();
+      grad[k].release();
+      value[k].release();
+      box[k].release();
+    }
+    shared_box.release();
+  }
+};
+}  // namespace cvp
+
 struct cvp_cv {
   int num_atoms = 0;
   cvp::KernelTimer timer;
+  cvp::HostPipeline host;
   int device = -1;  // device the spec's arrays live on (-1: not uploaded yet)
   int64_t workspace_limit = int64_t(1) << 30;
   std::vector<int32_t> active_atoms;  // sorted, unique
   cvp::DeviceBuffer workspace;
   virtual ~cvp_cv() {
     timer.clear();
+    host.release();
     workspace.release();
   }
   // Upload index/parameter arrays to the current device.

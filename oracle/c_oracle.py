@@ -40,6 +40,16 @@ def num_threads() -> int:
     return int(load().oracle_num_threads())
 
 
+def use_all_threads() -> int:
+    """Use every host thread this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        count = len(os.sched_getaffinity(0))
+    except AttributeError:
+        count = os.cpu_count() or 1
+    load().oracle_set_num_threads(C.c_int(count))
+    return num_threads()
+
+
 def contacts_batch(x, group1, group2, exclusions=(), box=None, r0=0.3, rc=0.6, rs=0.45,
                    step_kind=0, step_n=6, reference=1.0, need_grad=True):
     """NumberOfContacts of every frame of ``x`` [B, N, 3]; returns (value [B], grad [B, N, 3])."""

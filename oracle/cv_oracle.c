@@ -43,6 +43,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every host thread */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* step_kind: 0 = 1/(1+x^n), 1 = step(1-x) */
 static void step_function(int kind, int n, double x, double* s, double* ds) {
   if (kind == 1) {
