@@ -10,7 +10,7 @@ OBJECTS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(SOURCES))
 
 all: $(LIB) oracle
 
-$(OBJ)/%.o: $(SRC)/%.cu $(SRC)/common.cuh include/cvpack_b200.h
+$(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.cuh) include/cvpack_b200.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVCCFLAGS) $(EXTRA) -c $< -o $@
 

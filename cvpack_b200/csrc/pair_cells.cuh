@@ -29,8 +29,7 @@ constexpr int CELL_SORT_THREADS = 512;
 constexpr int CELL_MAX_AXIS = 16;      // cells per axis (<= 4096 cells)
 constexpr int CELL_MAX_CELLS = CELL_MAX_AXIS * CELL_MAX_AXIS * CELL_MAX_AXIS;
 constexpr int CELL_SWEEP_THREADS = 512;
-constexpr int CELL_BATCH = 8;          // clusters per staged batch (64 atoms, one 64-bit hit mask)
-constexpr int CELL_SMEM_BUDGET = 88 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
+constexpr int CELL_SMEM_BUDGET = 64 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
 constexpr int TAG_DUMMY = -1;
 
 __host__ __device__ inline int cell_round_up(int n, int m) { return (n + m - 1) / m * m; }
@@ -280,6 +279,15 @@ __host__ __device__ inline int cell_jchunk() {
   return (CELL_SMEM_BUDGET / per_atom) / CELL_TILE * CELL_TILE;
 }
 
+template <typename T>
+__host__ __device__ inline size_t cell_sweep_smem() {
+  using T4 = typename Vec4<T>::type;
+  const int jchunk = cell_jchunk<T>();
+  const int batch_atoms = (sizeof(T) == 4 ? 16 : 8) * CELL_CLUSTER;
+  return sizeof(T4) * ((size_t)jchunk + (size_t)(jchunk / CELL_CLUSTER) * 2 +
+                       (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms + 32));
+}
+
 // grid = B * nsplit CTAs; CTA (b, part) owns the i tiles part, part + nsplit, ... (strided by warp).
 template <typename T, int KIND, int PBC, bool OVERLAP, bool GRAD, bool FAST6>
 __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
@@ -300,11 +308,16 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   extern __shared__ __align__(128) unsigned char sweep_smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ double scratch[NCH * NWARP];
-  __shared__ __align__(16) T4 stage[NWARP][CELL_BATCH * CELL_CLUSTER];
+  // staged batch: 128 atoms (4 hit words) in FP32, 64 atoms in FP64 (same bytes)
+  constexpr int BATCH_CL = sizeof(T) == 4 ? 16 : 8;
+  constexpr int NW = BATCH_CL * CELL_CLUSTER / 32;
+  constexpr int BATCH_ATOMS = BATCH_CL * CELL_CLUSTER;
 
   const int jchunk = cell_jchunk<T>();
   T4* jsm = reinterpret_cast<T4*>(sweep_smem);
   T4* bsm = jsm + jchunk;  // cluster boxes of the chunk: (centre, half) pairs
+  T4* stage_all = bsm + (jchunk / CELL_CLUSTER) * 2;       // [NWARP][BATCH_ATOMS]
+  T4* survivors_all = stage_all + NWARP * BATCH_ATOMS;    // [NWARP][32]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.x / nsplit;
@@ -360,8 +373,11 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
     phase ^= 1u;
 
     for (int tile = warp_global; tile < ntile; tile += warp_stride) {
-      const T4 pi = ip[tile * CELL_TILE + lane];
+      T4 pi = ip[tile * CELL_TILE + lane];
       const int tagi = tag_decode(pi.w);
+      // padding lanes go to the far side of the padding atoms (+1e18), so no pair of them ever
+      // passes a distance test
+      if (tagi < 0) pi.x = pi.y = pi.z = T(-1e18);
       T4 qi;
       if (PRM) qi = atom_params[max(tagi, 0) & TAG_INDEX_MASK];
       T gx = T(0), gy = T(0), gz = T(0);
@@ -397,15 +413,18 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         hi[c] = T(0.5) * (mx[c] - mn[c]);
       }
 
-      // A *batch* = up to CELL_BATCH surviving clusters (64 atoms), copied -- already shifted to the
-      // right periodic image -- into this warp's staging buffer.  Phase 1 tests every staged atom
-      // against the lane's i atom and records hits in a 64-bit mask; phase 2 lets every lane walk
-      // its own hits, so the expensive pair function runs for real contacts only.  The larger the
-      // batch, the closer the busiest lane is to the average one.
-      uint32_t hits_lo = 0, hits_hi = 0;  // staged atoms 0..31 / 32..63
-      int nbatch = 0;
+      // A *batch* = up to BATCH_CL surviving clusters (128 atoms in FP32), copied -- already shifted
+      // to the right periodic image -- into this warp's staging buffer.  Phase 1 tests every staged
+      // atom against the lane's i atom and records hits in NW 32-bit masks; phase 2 lets every lane
+      // walk its own hits, so the expensive pair function runs for real contacts only.  The larger
+      // the batch, the closer the busiest lane is to the average one.
+      uint32_t hits[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) hits[w] = 0u;
+      int nbatch = 0;  // clusters staged so far
       bool batch_unsafe = false;
-      T4* stg = &stage[warp][0];
+      T4* stg = stage_all + warp * BATCH_ATOMS;
+      T4* lst = survivors_all + warp * 32;
       auto run_phases = [&](auto unsafe_tag) {
         constexpr bool UNSAFE = decltype(unsafe_tag)::value;
         auto test = [&](int slot) -> bool {
@@ -414,15 +433,14 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           if (UNSAFE) pair_min_image<PBC>(dx, dy, dz, bx);
           return fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2;
         };
-        if (nbatch == CELL_BATCH) {
+        if (nbatch == BATCH_CL) {
           // full batch: bit positions are compile-time constants
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            if (test(u)) hits_lo |= 1u << u;
-          }
+          for (int w = 0; w < NW; ++w) {
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            if (test(32 + u)) hits_hi |= 1u << u;
+            for (int u = 0; u < 32; ++u) {
+              if (test(w * 32 + u)) hits[w] |= 1u << u;
+            }
           }
         } else {
           for (int c = 0; c < nbatch; ++c) {
@@ -431,28 +449,40 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             for (int u = 0; u < CELL_CLUSTER; ++u) {
               if (test(c * CELL_CLUSTER + u)) m |= 1u << u;
             }
-            if (c < 4)
-              hits_lo |= m << (c * CELL_CLUSTER);
-            else
-              hits_hi |= m << ((c - 4) * CELL_CLUSTER);
+            m <<= (c & 3) * CELL_CLUSTER;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+              if ((c >> 2) == w) hits[w] |= m;
+            }
           }
         }
-        while (__any_sync(FULL, (hits_lo | hits_hi) != 0u)) {
-          if ((hits_lo | hits_hi) != 0u) {
-            int k;
-            if (hits_lo != 0u) {
-              k = __ffs(hits_lo) - 1;
-              hits_lo &= hits_lo - 1u;
-            } else {
-              k = 31 + __ffs(hits_hi);
-              hits_hi &= hits_hi - 1u;
+        int mine = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) mine += __popc(hits[w]);
+        const int rounds = __reduce_max_sync(FULL, mine);
+        for (int it = 0; it < rounds; ++it) {
+          int k = -1;
+#pragma unroll
+          for (int w = NW - 1; w >= 0; --w) {
+            if (hits[w] != 0u) k = w;
+          }
+          if (k >= 0) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+              if (k == w) {
+                k = w * 32 + __ffs(hits[w]) - 1;
+                hits[w] &= hits[w] - 1u;
+                break;
+              }
             }
             const T4 pj = stg[k];
             const int tagj = tag_decode(pj.w);
             T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
             if (UNSAFE) pair_min_image<PBC>(dx, dy, dz, bx);
             const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            bool ok = tagj >= 0 && tagi >= 0;
+            // padding never passes the shifted-image test (coordinates 1e18); the minimum-image
+            // reduction of the unsafe path can fold it back, so that path checks the tags
+            bool ok = UNSAFE ? (tagj >= 0 && tagi >= 0) : true;
             T w = T(1);
             if (OVERLAP) {
               if (((tagi ^ tagj) & TAG_INDEX_MASK) == 0) ok = false;
@@ -516,26 +546,40 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             // one shift serves every pair of (tile, cluster) iff ext <= L/2 - rc on this axis
             if (PBC == 1 && ext + rc > half_box[a]) safe = false;
           }
-          near = d2 < pc.cutoff2;
+          // clusters made of padding only sit at 1e18: the periodic shift would fold them back
+          near = d2 < pc.cutoff2 && cj.x < T(1e17);
         }
-        uint32_t cmask = __ballot_sync(FULL, near);
-        while (cmask != 0u) {
-          const int src = __ffs(cmask) - 1;
-          cmask &= cmask - 1u;
-          const int cl = c0 + src;
-          const T shx = __shfl_sync(FULL, sh[0], src);
-          const T shy = __shfl_sync(FULL, sh[1], src);
-          const T shz = __shfl_sync(FULL, sh[2], src);
-          batch_unsafe |= __shfl_sync(FULL, (int)safe, src) == 0;
-          if (lane < CELL_CLUSTER) {
-            T4 pj = jsm[cl * CELL_CLUSTER + lane];
-            pj.x -= shx;  // d = (x_j - shift) - x_i is the minimum image for a safe cluster
-            pj.y -= shy;
-            pj.z -= shz;
-            stg[nbatch * CELL_CLUSTER + lane] = pj;
+        // survivors of this window, compacted in cluster order: (shift, cluster index)
+        const uint32_t cmask = __ballot_sync(FULL, near);
+        if (cmask == 0u) continue;
+        const bool window_unsafe = __any_sync(FULL, near && !safe);
+        if (near) {
+          T4 ent;
+          ent.x = sh[0];
+          ent.y = sh[1];
+          ent.z = sh[2];
+          ent.w = tag_encode(c, T(0));
+          lst[__popc(cmask & ((1u << lane) - 1u))] = ent;
+        }
+        __syncwarp();
+        const int nsurv = __popc(cmask);
+        for (int s0 = 0; s0 < nsurv;) {
+          const int take = min(BATCH_CL - nbatch, nsurv - s0);
+          // stage `take` clusters, 4 per pass (one atom per lane)
+          for (int a = lane; a < take * CELL_CLUSTER; a += 32) {
+            const T4 ent = lst[s0 + (a >> 3)];
+            T4 pj = jsm[tag_decode(ent.w) * CELL_CLUSTER + (a & 7)];
+            pj.x -= ent.x;  // d = (x_j - shift) - x_i is the minimum image for a safe cluster
+            pj.y -= ent.y;
+            pj.z -= ent.z;
+            stg[nbatch * CELL_CLUSTER + a] = pj;
           }
-          if (++nbatch == CELL_BATCH) run_batch();
+          batch_unsafe |= window_unsafe;
+          nbatch += take;
+          s0 += take;
+          if (nbatch == BATCH_CL) run_batch();
         }
+        __syncwarp();  // the survivor list is rewritten by the next window
       }
       if (nbatch > 0) run_batch();
       if (GRAD) {

@@ -515,7 +515,8 @@ struct PairSumCV : cvp_cv {
       CVP_LAUNCH_CHECK();
     }
     const int jchunk = cell_jchunk<T>();
-    const size_t sweep_smem = (size_t)jchunk * sizeof(T4) + (size_t)(jchunk / CELL_CLUSTER) * 2 * sizeof(T4);
+    const size_t sweep_smem = cell_sweep_smem<T>();
+    (void)jchunk;
     auto sweep = [&](bool first, bool with_grad, const T* coef, double* energy) -> int {
       const T4* ip = first ? s1 : s2;
       const T4* jp = first ? s2 : s1;
