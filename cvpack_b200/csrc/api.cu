@@ -50,8 +50,9 @@ int check_args(cvp_cv* cv, int dtype, const void* positions, int box_mode, int64
                void* value) {
   CVP_REQUIRE(cv != nullptr, "null spec");
   CVP_REQUIRE(dtype == CVP_F32 || dtype == CVP_F64, "dtype must be CVP_F32 or CVP_F64");
-  CVP_REQUIRE(positions != nullptr && value != nullptr, "null positions or value buffer");
   CVP_REQUIRE(B >= 0, "negative frame count");
+  CVP_REQUIRE(B == 0 || (positions != nullptr && value != nullptr),
+              "null positions or value buffer");
   CVP_REQUIRE(N == cv->num_atoms, "the batch has " + std::to_string(N) +
                                       " atoms per frame but the spec was built for " +
                                       std::to_string(cv->num_atoms));

@@ -477,4 +477,18 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 
 inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Number of SMs of the current device (cached per device).
+inline int sm_count() {
+  static int cached[64] = {0};
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) return 148;
+  if (cached[device] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
+      sms = 148;
+    cached[device] = sms;
+  }
+  return cached[device];
+}
+
 }  // namespace cvp

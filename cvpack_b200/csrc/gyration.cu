@@ -7,6 +7,7 @@
 // Streaming, HBM-bound: coordinates are read once per pass, sums are carried in double (the
 // single-pass identity sum|r-c|^2 = sum|r|^2 - 2 c.sum r + n|c|^2 cancels badly in float).
 #include "common.cuh"
+#include "stream_fused.cuh"
 
 namespace cvp {
 namespace {
@@ -307,6 +308,93 @@ __global__ void __launch_bounds__(GYR_THREADS)
   }
 }
 
+// One-read fused evaluation of a contiguous FP32 group without a periodic box (stream_fused.cuh).
+// WEIGHTED: the centre is a weighted mean (weights = the per-atom auxiliary float); otherwise the
+// geometric centre, for which sum_i d_i vanishes and the gradient is f (r_k - c).
+template <bool WEIGHTED>
+struct GyrationFusedPolicy {
+  static constexpr int NS = WEIGHTED ? 7 : 4;
+  static constexpr int AUX = WEIGHTED ? 1 : 0;
+  struct Params {
+    int n;
+    int squared;
+  };
+  struct Frame {
+    float c[3];
+    float sw[3];
+    float f;
+    float pad[9];
+  };
+  __device__ static __forceinline__ void accumulate(const Params&, const float* aux,
+                                                    const float (&x)[4], const float (&y)[4],
+                                                    const float (&z)[4], double (&v)[NS]) {
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (WEIGHTED) {
+      const float4 wv = *reinterpret_cast<const float4*>(aux);  // shared memory
+      w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double xd = x[k], yd = y[k], zd = z[k];
+      v[0] += xd;
+      v[1] += yd;
+      v[2] += zd;
+      v[3] += xd * xd + yd * yd + zd * zd;
+      if (WEIGHTED) {
+        const double wd = w[k];
+        v[NS - 3] += wd * xd;
+        v[NS - 2] += wd * yd;
+        v[NS - 1] += wd * zd;
+      }
+    }
+  }
+  __device__ static __noinline__ void complete(const Params& p, const double (&sums)[NS],
+                                               Frame* frame, float* value, int accumulate) {
+    const double n = p.n;
+    double c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = WEIGHTED ? sums[NS - 3 + k] : sums[k] / n;
+    const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    const double cs = c[0] * sums[0] + c[1] * sums[1] + c[2] * sums[2];
+    const double rg2 = fmax(0.0, (sums[3] - 2.0 * cs + n * cc) / n);
+    const double rg = sqrt(rg2);
+    Frame fr;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      fr.c[k] = (float)c[k];
+      fr.sw[k] = WEIGHTED ? (float)(sums[k] - n * c[k]) : 0.f;
+    }
+    fr.f = (float)(p.squared ? 2.0 / n : (rg > 0.0 ? 1.0 / (n * rg) : 0.0));
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fr.pad[k] = 0.f;
+    *frame = fr;
+    const double result = p.squared ? rg2 : rg;
+    *value = accumulate ? (float)((double)*value + result) : (float)result;
+  }
+  __device__ static __forceinline__ void gradient(const Params&, const Frame& fr, const float* aux,
+                                                  const float (&x)[4], const float (&y)[4],
+                                                  const float (&z)[4], float (&gx)[4],
+                                                  float (&gy)[4], float (&gz)[4]) {
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (WEIGHTED) {
+      const float4 wv = *reinterpret_cast<const float4*>(aux);
+      w[0] = wv.x; w[1] = wv.y; w[2] = wv.z; w[3] = wv.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (WEIGHTED) {
+        gx[k] = fr.f * ((x[k] - fr.c[0]) - w[k] * fr.sw[0]);
+        gy[k] = fr.f * ((y[k] - fr.c[1]) - w[k] * fr.sw[1]);
+        gz[k] = fr.f * ((z[k] - fr.c[2]) - w[k] * fr.sw[2]);
+      } else {
+        gx[k] = fr.f * (x[k] - fr.c[0]);
+        gy[k] = fr.f * (y[k] - fr.c[1]);
+        gz[k] = fr.f * (z[k] - fr.c[2]);
+      }
+    }
+  }
+};
+
 struct GyrationCV : cvp_cv {
   bool uniform_weights = false;
   std::vector<float> weights_f32;
@@ -328,10 +416,49 @@ struct GyrationCV : cvp_cv {
     return cvp::upload(d_weights, weights);
   }
   int nslice() const { return (int)div_up((int64_t)group.size(), GYR_ATOMS_PER_BLOCK); }
+  int use_fused = 1;    // option "fused": one-read persistent kernel for the streaming fast path
+  int fused_lag = 3;    // option "fused_lag"
+  int fused_slice = 0;  // option "fused_slice"
   size_t workspace_per_frame(int, bool) const override {
-    return (size_t)nslice() * 7 * sizeof(double) + sizeof(GyrationFrame) + 64;
+    return std::max((size_t)nslice() * 7 * sizeof(double) + sizeof(GyrationFrame) + 64,
+                    FusedLaunch<GyrationFusedPolicy<true>>::workspace_per_frame((int)group.size()));
   }
-  size_t workspace_fixed(int) const override { return 4 * 256; }
+  size_t workspace_fixed(int) const override {
+    return 4 * 256 + FusedLaunch<GyrationFusedPolicy<true>>::workspace_fixed();
+  }
+  int set_option(const char* name, int value) override {
+    const std::string key(name);
+    if (key == "fused") {
+      std::swap(use_fused, value);
+      return value;
+    }
+    if (key == "fused_lag") {
+      std::swap(fused_lag, value);
+      return value;
+    }
+    if (key == "fused_slice") {
+      std::swap(fused_slice, value);
+      return value;
+    }
+    return cvp_cv::set_option(name, value);
+  }
+  template <typename Policy>
+  int run_fused(const FusedGeom& geom, const EvalArgs& a, void* ws, const float* aux) {
+    typename Policy::Params params;
+    params.n = (int)group.size();
+    params.squared = squared;
+    const bool accumulate = (a.flags & CVP_FLAG_ACCUMULATE) != 0;
+    const bool dense = (int64_t)group.size() == a.num_atoms;
+    if (a.grad != nullptr && !accumulate && !dense)
+      CVP_CUDA_CHECK(cudaMemsetAsync(a.grad, 0, (size_t)a.num_frames * a.num_atoms * 3 * sizeof(float),
+                                     a.stream));
+    timer.begin("gyration_fused", a.stream);
+    int status = FusedLaunch<Policy>::launch(static_cast<const float*>(a.positions), aux, geom,
+                                             sm_count(), params, ws, static_cast<float*>(a.value),
+                                             static_cast<float*>(a.grad), accumulate, a.stream);
+    timer.end(a.stream);
+    return status;
+  }
   int64_t max_frames_per_run() const override {
     return std::max<int64_t>(1, (int64_t(1) << 31) / nslice() - 1);
   }
@@ -356,12 +483,25 @@ struct GyrationCV : cvp_cv {
     const unsigned grid = (unsigned)(B * ns);
     const int warp_blocks = (int)div_up(B * 32, 128);
 
-    timer.begin("gyration_sums", st);
     // streaming fast path: FP32, no box, contiguous group starting on a 16-byte boundary
     const bool use_fast = PBC == 0 && std::is_same<T, float>::value && contiguous && n % 4 == 0 &&
                           first % 4 == 0 && N % 4 == 0;
     const int fast_ns = (int)div_up(n, GYR_FAST_SLICE);
     const float* wf = uniform_weights ? nullptr : static_cast<const float*>(d_weights_f32.ptr);
+    if (use_fast && use_fused && B >= 64) {
+      FusedGeom geom;
+      if (uniform_weights) {
+        if (FusedLaunch<GyrationFusedPolicy<false>>::plan(n, N, first, B, grad != nullptr, fused_lag,
+                                                          fused_slice, sm_count(), &geom)) {
+          return run_fused<GyrationFusedPolicy<false>>(geom, a, ws, nullptr);
+        }
+      } else if (FusedLaunch<GyrationFusedPolicy<true>>::plan(n, N, first, B, grad != nullptr,
+                                                              fused_lag, fused_slice, sm_count(),
+                                                              &geom)) {
+        return run_fused<GyrationFusedPolicy<true>>(geom, a, ws, wf);
+      }
+    }
+    timer.begin("gyration_sums", st);
     if (use_fast)
       gyration_sums_fast_kernel<<<(unsigned)(B * fast_ns), GYR_THREADS, 0, st>>>(
           reinterpret_cast<const float*>(pos), N, first, n, wf, fast_ns, partials);

@@ -22,6 +22,7 @@
 //   combine   one thread per frame: CV value and d CV / d rmsd_g
 //   gradient  one thread per (frame, active atom): sum over the atom's entries (CSR), single writer
 #include "common.cuh"
+#include "stream_fused.cuh"
 
 namespace cvp {
 namespace {
@@ -190,6 +191,197 @@ __device__ inline void jacobi4_max(double (&a)[4][4], double& lambda, double (&q
 #pragma unroll
   for (int k = 0; k < 4; ++k) q[k] = v[k][best];
 }
+
+// Largest eigenpair of Horn's matrix the fast way (Theobald's QCP idea): Newton iteration on the
+// characteristic polynomial from lambda0 = (Gx+Gy)/2 >= lambda_max (monotone convergence), with the
+// polynomial coefficients taken from power traces (F is traceless), then the eigenvector as a
+// column of adj(F - lambda I).  Returns false when the eigenvalue is (nearly) degenerate and the
+// adjugate vanishes; the caller then falls back to Jacobi.
+__device__ inline double det3(double a, double b, double c, double d, double e, double f, double g,
+                              double h, double i) {
+  return a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+}
+
+// cofactor (ROW, COL) of a 4x4 matrix with compile-time indices (registers only)
+template <int ROW, int COL>
+__device__ __forceinline__ double cofactor4(const double (&a)[4][4]) {
+  constexpr int r0 = ROW == 0 ? 1 : 0, r1 = ROW <= 1 ? 2 : 1, r2 = ROW <= 2 ? 3 : 2;
+  constexpr int c0 = COL == 0 ? 1 : 0, c1 = COL <= 1 ? 2 : 1, c2 = COL <= 2 ? 3 : 2;
+  const double d = det3(a[r0][c0], a[r0][c1], a[r0][c2], a[r1][c0], a[r1][c1], a[r1][c2], a[r2][c0],
+                        a[r2][c1], a[r2][c2]);
+  return ((ROW + COL) & 1) ? -d : d;
+}
+template <int ROW>
+__device__ __forceinline__ void cofactor_row4(const double (&a)[4][4], double (&q)[4]) {
+  q[0] = cofactor4<ROW, 0>(a);
+  q[1] = cofactor4<ROW, 1>(a);
+  q[2] = cofactor4<ROW, 2>(a);
+  q[3] = cofactor4<ROW, 3>(a);
+}
+
+__device__ inline bool qcp4_max(const double (&f)[4][4], double lambda0, double& lambda,
+                                double (&q)[4]) {
+  double f2[4][4];
+  double t2 = 0.0, t3 = 0.0, t4 = 0.0, scale = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i; j < 4; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += f[i][k] * f[k][j];
+      f2[i][j] = f2[j][i] = s;
+      scale = fmax(scale, fabs(f[i][j]));
+    }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      t2 += f[i][j] * f[i][j];
+      t3 += f2[i][j] * f[i][j];
+      t4 += f2[i][j] * f2[i][j];
+    }
+  if (scale == 0.0) return false;
+  const double c2 = -0.5 * t2, c1 = -t3 / 3.0, c0 = 0.25 * (0.5 * t2 * t2 - t4);
+  // Newton from above: p > 0 and p' > 0 all the way down to the largest root, so the iterates
+  // decrease monotonically; stop when the step drowns in rounding (or changes sign).
+  double x = lambda0;
+  for (int it = 0; it < 48; ++it) {
+    const double x2 = x * x;
+    const double p = (x2 + c2) * x2 + c1 * x + c0;
+    const double dp = (4.0 * x2 + 2.0 * c2) * x + c1;
+    if (!(dp > 0.0)) break;
+    const double step = p / dp;
+    if (!(step > 4e-16 * x)) break;
+    x -= step;
+  }
+  lambda = x;
+  double a[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[i][j] = f[i][j] - (i == j ? x : 0.0);
+  // adj(A) = c q q^T for a rank-3 A: the row with the largest diagonal cofactor is the best
+  // conditioned copy of the eigenvector
+  double row[4][4];
+  cofactor_row4<0>(a, row[0]);
+  cofactor_row4<1>(a, row[1]);
+  cofactor_row4<2>(a, row[2]);
+  cofactor_row4<3>(a, row[3]);
+  double diag_best = fabs(row[0][0]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = row[0][k];
+#pragma unroll
+  for (int j = 1; j < 4; ++j) {
+    const bool better = fabs(row[j][j]) > diag_best;
+    diag_best = better ? fabs(row[j][j]) : diag_best;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = better ? row[j][k] : q[k];
+  }
+  return diag_best > 1e-10 * scale * scale * scale;
+}
+
+// rmsd and U^T from the 13 sums of a single-segment group
+__device__ inline void rmsd_from_sums(const double* sums, double gy, int n, bool allow_qcp,
+                                      double& rmsd, double (&ut)[9], double (&centroid)[3]) {
+  const double inv = 1.0 / n;
+  const double gx = sums[3] - (sums[0] * sums[0] + sums[1] * sums[1] + sums[2] * sums[2]) * inv;
+  centroid[0] = sums[0] * inv;
+  centroid[1] = sums[1] * inv;
+  centroid[2] = sums[2] * inv;
+  const double Sxx = sums[4], Sxy = sums[5], Sxz = sums[6], Syx = sums[7], Syy = sums[8],
+               Syz = sums[9], Szx = sums[10], Szy = sums[11], Szz = sums[12];
+  double f[4][4] = {{Sxx + Syy + Szz, Syz - Szy, Szx - Sxz, Sxy - Syx},
+                    {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
+                    {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
+                    {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
+  double lambda, q[4];
+  if (!allow_qcp || !qcp4_max(f, 0.5 * (gx + gy), lambda, q)) jacobi4_max(f, lambda, q);
+  const double norm = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double q0 = q[0] * norm, q1 = q[1] * norm, q2 = q[2] * norm, q3 = q[3] * norm;
+  const double msd = (gx + gy - 2.0 * lambda) * inv;
+  rmsd = msd < 1e-20 ? 0.0 : sqrt(msd);
+  ut[0] = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3;
+  ut[1] = 2 * (q1 * q2 + q0 * q3);
+  ut[2] = 2 * (q1 * q3 - q0 * q2);
+  ut[3] = 2 * (q1 * q2 - q0 * q3);
+  ut[4] = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3;
+  ut[5] = 2 * (q2 * q3 + q0 * q1);
+  ut[6] = 2 * (q1 * q3 + q0 * q2);
+  ut[7] = 2 * (q2 * q3 - q0 * q1);
+  ut[8] = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+}
+
+// One-read fused evaluation of a contiguous FP32 group (stream_fused.cuh).
+struct RmsdFusedPolicy {
+  static constexpr int NS = 13;
+  static constexpr int AUX = 3;  // per-atom auxiliary data: the centred reference, float [n][3]
+  struct Params {
+    double gy;  // sum |y^|^2 of that reference
+    int n;
+  };
+  struct Frame {
+    float c[3];
+    float ut[9];
+    float f;
+    float pad[3];
+  };
+  __device__ static __forceinline__ void accumulate(const Params&, const float* aux,
+                                                    const float (&x)[4], const float (&y)[4],
+                                                    const float (&z)[4], double (&v)[NS]) {
+    const float4* py = reinterpret_cast<const float4*>(aux);  // shared memory
+    const float4 r0 = py[0], r1 = py[1], r2 = py[2];
+    float rx[4], ry[4], rz[4];
+    fused_unpack4(r0, r1, r2, rx, ry, rz);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double xd = x[k], yd = y[k], zd = z[k], rxd = rx[k], ryd = ry[k], rzd = rz[k];
+      v[0] += xd;
+      v[1] += yd;
+      v[2] += zd;
+      v[3] += xd * xd + yd * yd + zd * zd;
+      v[4] += xd * rxd;
+      v[5] += xd * ryd;
+      v[6] += xd * rzd;
+      v[7] += yd * rxd;
+      v[8] += yd * ryd;
+      v[9] += yd * rzd;
+      v[10] += zd * rxd;
+      v[11] += zd * ryd;
+      v[12] += zd * rzd;
+    }
+  }
+  // kept out of line so that the solver's registers do not limit the occupancy of the streaming loops
+  __device__ static __noinline__ void complete(const Params& p, const double (&sums)[NS],
+                                               Frame* frame, float* value, int accumulate) {
+    double rmsd, ut[9], c[3];
+    rmsd_from_sums(sums, p.gy, p.n, true, rmsd, ut, c);
+    Frame fr;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fr.ut[k] = (float)ut[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fr.c[k] = (float)c[k];
+    fr.f = rmsd > 0.0 ? (float)(1.0 / (p.n * rmsd)) : 0.f;
+    fr.pad[0] = fr.pad[1] = fr.pad[2] = 0.f;
+    *frame = fr;
+    *value = accumulate ? *value + (float)rmsd : (float)rmsd;
+  }
+  __device__ static __forceinline__ void gradient(const Params&, const Frame& fr, const float* aux,
+                                                  const float (&x)[4], const float (&y)[4],
+                                                  const float (&z)[4], float (&gx)[4],
+                                                  float (&gy)[4], float (&gz)[4]) {
+    const float4* py = reinterpret_cast<const float4*>(aux);  // shared memory
+    const float4 r0 = py[0], r1 = py[1], r2 = py[2];
+    float rx[4], ry[4], rz[4];
+    fused_unpack4(r0, r1, r2, rx, ry, rz);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gx[k] = fr.f * ((x[k] - fr.c[0]) - (fr.ut[0] * rx[k] + fr.ut[1] * ry[k] + fr.ut[2] * rz[k]));
+      gy[k] = fr.f * ((y[k] - fr.c[1]) - (fr.ut[3] * rx[k] + fr.ut[4] * ry[k] + fr.ut[5] * rz[k]));
+      gz[k] = fr.f * ((z[k] - fr.c[2]) - (fr.ut[6] * rx[k] + fr.ut[7] * ry[k] + fr.ut[8] * rz[k]));
+    }
+  }
+};
 
 // Per (frame, group) result.
 struct RmsdSolution {
@@ -408,6 +600,9 @@ __global__ void __launch_bounds__(RMSD_FAST_THREADS)
 struct RmsdCV : cvp_cv {
   // streaming fast path (see rmsd_sums_fast_kernel)
   bool fast = false;
+  int use_fused = 1;    // option "fused": one-read persistent kernel for the streaming fast path
+  int fused_lag = 3;    // option "fused_lag": rounds between the sums and the gradient of a frame
+  int fused_slice = 0;  // option "fused_slice": atoms per sub-slice (0 = chosen by the planner)
   int fast_first = 0, fast_nslice = 0;
   std::vector<float> ref_f32;
   std::vector<int32_t> fast_seg_slice_offsets;
@@ -458,10 +653,29 @@ struct RmsdCV : cvp_cv {
     return CVP_OK;
   }
   size_t workspace_per_frame(int, bool) const override {
-    return (size_t)std::max(nslice, fast_nslice) * 13 * sizeof(double) + (size_t)num_groups * sizeof(RmsdSolution) +
+    return FusedLaunch<RmsdFusedPolicy>::workspace_per_frame((int)num_entries) +
+           (size_t)std::max(nslice, fast_nslice) * 13 * sizeof(double) + (size_t)num_groups * sizeof(RmsdSolution) +
            (size_t)nseg * 3 * sizeof(double) + (size_t)num_groups * sizeof(double) + 64;
   }
-  size_t workspace_fixed(int) const override { return 6 * 256; }
+  size_t workspace_fixed(int) const override {
+    return 6 * 256 + FusedLaunch<RmsdFusedPolicy>::workspace_fixed();
+  }
+  int set_option(const char* name, int value) override {
+    const std::string key(name);
+    if (key == "fused") {
+      std::swap(use_fused, value);
+      return value;
+    }
+    if (key == "fused_lag") {
+      std::swap(fused_lag, value);
+      return value;
+    }
+    if (key == "fused_slice") {
+      std::swap(fused_slice, value);
+      return value;
+    }
+    return cvp_cv::set_option(name, value);
+  }
   int64_t max_frames_per_run() const override {
     int64_t per_frame = std::max<int64_t>(nslice, (int64_t)active_atoms.size() / 64 + 1);
     return std::max<int64_t>(1, (int64_t(1) << 30) / per_frame);
@@ -483,6 +697,23 @@ struct RmsdCV : cvp_cv {
 
     // streaming fast path: FP32, one contiguous aligned group
     const bool use_fast = fast && std::is_same<T, float>::value && (N % 4) == 0;
+    FusedGeom geom;
+    if (use_fast && use_fused && cp.mode == CVP_COMBINE_IDENTITY && B >= 64 &&
+        FusedLaunch<RmsdFusedPolicy>::plan((int)num_entries, N, fast_first, B, grad != nullptr,
+                                           fused_lag, fused_slice, sm_count(), &geom)) {
+      RmsdFusedPolicy::Params params;
+      params.gy = fast_gy[0];
+      params.n = (int)num_entries;
+      if (grad != nullptr && !accumulate && !dense)
+        CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+      timer.begin("rmsd_fused", st);
+      int status = FusedLaunch<RmsdFusedPolicy>::launch(
+          reinterpret_cast<const float*>(pos), static_cast<const float*>(d_ref_f32.ptr), geom,
+          sm_count(), params, ws, reinterpret_cast<float*>(value), reinterpret_cast<float*>(grad),
+          accumulate, st);
+      timer.end(st);
+      return status;
+    }
     const int ns = use_fast ? fast_nslice : nslice;
     if (use_fast) {
       timer.begin("rmsd_sums", st);
@@ -503,6 +734,7 @@ struct RmsdCV : cvp_cv {
     }
     {
       int64_t total = B * num_groups;
+      timer.begin("rmsd_solve", st);
       rmsd_solve_kernel<<<(unsigned)div_up(total, 64), 64, 0, st>>>(
           partials, ns, static_cast<const int32_t*>(d_group_seg_offsets.ptr),
           static_cast<const int32_t*>(use_fast ? d_fast_seg_slice_offsets.ptr
@@ -511,6 +743,7 @@ struct RmsdCV : cvp_cv {
           static_cast<const int32_t*>(d_group_size.ptr),
           static_cast<const double*>(use_fast ? d_fast_gy.ptr : d_group_gy.ptr), num_groups, B,
           solution, seg_centroid, nseg);
+      timer.end(st);
       CVP_LAUNCH_CHECK();
     }
     rmsd_combine_kernel<T><<<(unsigned)div_up(B, 128), 128, 0, st>>>(

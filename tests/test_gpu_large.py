@@ -165,3 +165,70 @@ def test_rmsd_full_size_properties():
     stored = ctx.getPositions().double().cpu().numpy()
     ref_rg, _ = c_oracle.gyration_batch(stored, np.arange(n), need_grad=False)
     assert np.allclose(rgv, ref_rg, rtol=1e-6)
+
+
+@pytest.mark.parametrize(
+    "n,first,frames,sub,lag",
+    [
+        (20000, 0, 150, 0, 3),      # planner's choice; 150 frames is not a multiple of a round
+        (20000, 0, 150, 128, 1),    # smallest sub-slices, shortest lag
+        (6000, 2000, 700, 256, 2),  # contiguous part of the frame (zero gradient elsewhere)
+        (3076, 4, 333, 1024, 5),    # ragged last sub-slice and chunk
+    ],
+)
+def test_fused_streaming_kernel_vs_c_oracle(n, first, frames, sub, lag):
+    """The one-read persistent kernel (stream_fused.cuh) behind RMSD and RadiusOfGyration: batches
+    of at least 64 frames of a contiguous group take it; compared with the C oracle and, for the
+    same inputs, with the two-pass kernels."""
+    rng = np.random.default_rng(35)
+    total = first + n + 8
+    reference = 2.0 * rng.normal(size=(total, 3))
+    from scipy.spatial.transform import Rotation
+
+    rot = Rotation.random(frames, random_state=3).as_matrix()
+    x = np.einsum("bij,nj->bni", rot, reference) + 0.05 * rng.normal(size=(frames, total, 3))
+    x += rng.normal(size=(frames, 1, 3))
+    system = helpers.make_system(total, rng)
+    atoms = np.arange(first, first + n)
+    rmsd = cvpack.RMSD(reference, atoms, total)
+    rg = cvpack.RadiusOfGyration(atoms)
+    rg_mass = cvpack.RadiusOfGyrationSq(atoms, weighByMass=True)
+    for cv in (rmsd, rg, rg_mass):
+        cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x)
+    stored = ctx.getPositions().double().cpu().numpy()
+    masses = system.getMasses()[atoms]
+    cases = [
+        (rmsd, "rmsd_fused", c_oracle.rmsd_batch(stored, atoms, reference[atoms])),
+        (rg, "gyration_fused", c_oracle.gyration_batch(stored, atoms)),
+        (rg_mass, "gyration_fused",
+         c_oracle.gyration_batch(stored, atoms, masses / masses.sum(), squared=True)),
+    ]
+    for cv, kernel, (ref_value, ref_grad) in cases:
+        native = ctx._native_cv(cv)  # pylint: disable=protected-access
+        native.set_option("fused_slice", sub)
+        native.set_option("fused_lag", lag)
+        native.set_option("time_kernels", 1)
+        value, grad = cv.getValueAndGradient(ctx)
+        assert native.kernel_time(kernel)[1] == 1, "the fused kernel did not run"
+        v = value._value.double().cpu().numpy()
+        g = grad.double().cpu().numpy()
+        assert np.abs(v - ref_value).max() <= 1e-5 * np.abs(ref_value).max(), cv.getName()
+        assert np.abs(g - ref_grad).max() <= 1e-5 * np.abs(ref_grad).max(), cv.getName()
+        outside = np.ones(total, dtype=bool)
+        outside[atoms] = False
+        assert not g[:, outside].any()
+        # value only (no gradient items, no lag)
+        v_only = cv.getValue(ctx)._value
+        assert torch.equal(v_only, value._value)
+        assert native.kernel_time(kernel)[1] == 1
+        # the same through the two-pass kernels
+        native.set_option("fused", 0)
+        value2, grad2 = cv.getValueAndGradient(ctx)
+        assert native.kernel_time(kernel)[1] == 0
+        native.set_option("fused", 1)
+        assert torch.allclose(value2._value, value._value, rtol=1e-6)
+        assert (grad2 - grad).abs().max() <= 2e-6 * grad.abs().max()
+        # deterministic
+        value3, grad3 = cv.getValueAndGradient(ctx)
+        assert torch.equal(value3._value, value._value) and torch.equal(grad3, grad)
