@@ -315,6 +315,7 @@ template <bool WEIGHTED>
 struct GyrationFusedPolicy {
   static constexpr int NS = WEIGHTED ? 7 : 4;
   static constexpr int AUX = WEIGHTED ? 1 : 0;
+  static constexpr int AUXD = 0;
   struct Params {
     int n;
     int squared;
@@ -325,7 +326,7 @@ struct GyrationFusedPolicy {
     float f;
     float pad[9];
   };
-  __device__ static __forceinline__ void accumulate(const Params&, const float* aux,
+  __device__ static __forceinline__ void accumulate(const Params&, const float* aux, const double2*,
                                                     const float (&x)[4], const float (&y)[4],
                                                     const float (&z)[4], double (&v)[NS]) {
     float w[4] = {0.f, 0.f, 0.f, 0.f};
@@ -339,7 +340,9 @@ struct GyrationFusedPolicy {
       v[0] += xd;
       v[1] += yd;
       v[2] += zd;
-      v[3] += xd * xd + yd * yd + zd * zd;
+      v[3] = fma(xd, xd, v[3]);
+      v[3] = fma(yd, yd, v[3]);
+      v[3] = fma(zd, zd, v[3]);
       if (WEIGHTED) {
         const double wd = w[k];
         v[NS - 3] += wd * xd;
@@ -419,6 +422,8 @@ struct GyrationCV : cvp_cv {
   int use_fused = 1;    // option "fused": one-read persistent kernel for the streaming fast path
   int fused_lag = 3;    // option "fused_lag"
   int fused_slice = 0;  // option "fused_slice"
+  int fused_slots = 0;  // option "fused_slots"
+  int fused_hints = 3;  // option "fused_hints"
   size_t workspace_per_frame(int, bool) const override {
     return std::max((size_t)nslice() * 7 * sizeof(double) + sizeof(GyrationFrame) + 64,
                     FusedLaunch<GyrationFusedPolicy<true>>::workspace_per_frame((int)group.size()));
@@ -440,6 +445,14 @@ struct GyrationCV : cvp_cv {
       std::swap(fused_slice, value);
       return value;
     }
+    if (key == "fused_slots") {
+      std::swap(fused_slots, value);
+      return value;
+    }
+    if (key == "fused_hints") {
+      std::swap(fused_hints, value);
+      return value;
+    }
     return cvp_cv::set_option(name, value);
   }
   template <typename Policy>
@@ -453,8 +466,8 @@ struct GyrationCV : cvp_cv {
       CVP_CUDA_CHECK(cudaMemsetAsync(a.grad, 0, (size_t)a.num_frames * a.num_atoms * 3 * sizeof(float),
                                      a.stream));
     timer.begin("gyration_fused", a.stream);
-    int status = FusedLaunch<Policy>::launch(static_cast<const float*>(a.positions), aux, geom,
-                                             sm_count(), params, ws, static_cast<float*>(a.value),
+    int status = FusedLaunch<Policy>::launch(static_cast<const float*>(a.positions), aux, nullptr,
+                                             geom, sm_count(), params, ws, static_cast<float*>(a.value),
                                              static_cast<float*>(a.grad), accumulate, a.stream);
     timer.end(a.stream);
     return status;
@@ -491,12 +504,11 @@ struct GyrationCV : cvp_cv {
     if (use_fast && use_fused && B >= 64) {
       FusedGeom geom;
       if (uniform_weights) {
-        if (FusedLaunch<GyrationFusedPolicy<false>>::plan(n, N, first, B, grad != nullptr, fused_lag,
-                                                          fused_slice, sm_count(), &geom)) {
+        if (FusedLaunch<GyrationFusedPolicy<false>>::plan(n, N, first, B, grad != nullptr, fused_lag, fused_slice, fused_slots, fused_hints, sm_count(), &geom)) {
           return run_fused<GyrationFusedPolicy<false>>(geom, a, ws, nullptr);
         }
       } else if (FusedLaunch<GyrationFusedPolicy<true>>::plan(n, N, first, B, grad != nullptr,
-                                                              fused_lag, fused_slice, sm_count(),
+                                                              fused_lag, fused_slice, fused_slots, fused_hints, sm_count(),
                                                               &geom)) {
         return run_fused<GyrationFusedPolicy<true>>(geom, a, ws, wf);
       }

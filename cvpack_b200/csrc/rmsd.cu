@@ -315,53 +315,59 @@ __device__ inline void rmsd_from_sums(const double* sums, double gy, int n, bool
 // One-read fused evaluation of a contiguous FP32 group (stream_fused.cuh).
 struct RmsdFusedPolicy {
   static constexpr int NS = 13;
-  static constexpr int AUX = 3;  // per-atom auxiliary data: the centred reference, float [n][3]
+  static constexpr int AUX = 3;   // per-atom auxiliary data: the centred reference, float [n][3]
+  static constexpr int AUXD = 3;  // ... and the same values as doubles for the sums
   struct Params {
     double gy;  // sum |y^|^2 of that reference
     int n;
   };
   struct Frame {
-    float c[3];
-    float ut[9];
-    float f;
+    float c[3];   // centroid
+    float ut[9];  // U^T
+    float f;      // 1 / (n rmsd)
     float pad[3];
   };
-  __device__ static __forceinline__ void accumulate(const Params&, const float* aux,
+  __device__ static __forceinline__ void accumulate(const Params&, const float*, const double2* auxd,
                                                     const float (&x)[4], const float (&y)[4],
                                                     const float (&z)[4], double (&v)[NS]) {
-    const float4* py = reinterpret_cast<const float4*>(aux);  // shared memory
-    const float4 r0 = py[0], r1 = py[1], r2 = py[2];
-    float rx[4], ry[4], rz[4];
-    fused_unpack4(r0, r1, r2, rx, ry, rz);
+    // shared memory, conflict-free: (r0x r0y) (r0z r1x) (r1y r1z) (r2x r2y) (r2z r3x) (r3y r3z)
+    const double2 p0 = auxd[0], p1 = auxd[32], p2 = auxd[64], p3 = auxd[96], p4 = auxd[128],
+                  p5 = auxd[160];
+    const double rx[4] = {p0.x, p1.y, p3.x, p4.y};
+    const double ry[4] = {p0.y, p2.x, p3.y, p5.x};
+    const double rz[4] = {p1.x, p2.y, p4.x, p5.y};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const double xd = x[k], yd = y[k], zd = z[k], rxd = rx[k], ryd = ry[k], rzd = rz[k];
+      const double xd = x[k], yd = y[k], zd = z[k];
       v[0] += xd;
       v[1] += yd;
       v[2] += zd;
-      v[3] += xd * xd + yd * yd + zd * zd;
-      v[4] += xd * rxd;
-      v[5] += xd * ryd;
-      v[6] += xd * rzd;
-      v[7] += yd * rxd;
-      v[8] += yd * ryd;
-      v[9] += yd * rzd;
-      v[10] += zd * rxd;
-      v[11] += zd * ryd;
-      v[12] += zd * rzd;
+      v[3] = fma(xd, xd, v[3]);
+      v[3] = fma(yd, yd, v[3]);
+      v[3] = fma(zd, zd, v[3]);
+      v[4] = fma(xd, rx[k], v[4]);
+      v[5] = fma(xd, ry[k], v[5]);
+      v[6] = fma(xd, rz[k], v[6]);
+      v[7] = fma(yd, rx[k], v[7]);
+      v[8] = fma(yd, ry[k], v[8]);
+      v[9] = fma(yd, rz[k], v[9]);
+      v[10] = fma(zd, rx[k], v[10]);
+      v[11] = fma(zd, ry[k], v[11]);
+      v[12] = fma(zd, rz[k], v[12]);
     }
   }
-  // kept out of line so that the solver's registers do not limit the occupancy of the streaming loops
+  // kept out of line so that the solver's registers do not burden the streaming loops
   __device__ static __noinline__ void complete(const Params& p, const double (&sums)[NS],
                                                Frame* frame, float* value, int accumulate) {
     double rmsd, ut[9], c[3];
     rmsd_from_sums(sums, p.gy, p.n, true, rmsd, ut, c);
+    const double f = rmsd > 0.0 ? 1.0 / (p.n * rmsd) : 0.0;
     Frame fr;
 #pragma unroll
     for (int k = 0; k < 9; ++k) fr.ut[k] = (float)ut[k];
 #pragma unroll
     for (int k = 0; k < 3; ++k) fr.c[k] = (float)c[k];
-    fr.f = rmsd > 0.0 ? (float)(1.0 / (p.n * rmsd)) : 0.f;
+    fr.f = (float)f;
     fr.pad[0] = fr.pad[1] = fr.pad[2] = 0.f;
     *frame = fr;
     *value = accumulate ? *value + (float)rmsd : (float)rmsd;
@@ -376,9 +382,10 @@ struct RmsdFusedPolicy {
     fused_unpack4(r0, r1, r2, rx, ry, rz);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      gx[k] = fr.f * ((x[k] - fr.c[0]) - (fr.ut[0] * rx[k] + fr.ut[1] * ry[k] + fr.ut[2] * rz[k]));
-      gy[k] = fr.f * ((y[k] - fr.c[1]) - (fr.ut[3] * rx[k] + fr.ut[4] * ry[k] + fr.ut[5] * rz[k]));
-      gz[k] = fr.f * ((z[k] - fr.c[2]) - (fr.ut[6] * rx[k] + fr.ut[7] * ry[k] + fr.ut[8] * rz[k]));
+      // f ((x - c) - U^T y): one rounding per step, the products are not rounded on their own
+      gx[k] = fr.f * fmaf(-fr.ut[0], rx[k], fmaf(-fr.ut[1], ry[k], fmaf(-fr.ut[2], rz[k], x[k] - fr.c[0])));
+      gy[k] = fr.f * fmaf(-fr.ut[3], rx[k], fmaf(-fr.ut[4], ry[k], fmaf(-fr.ut[5], rz[k], y[k] - fr.c[1])));
+      gz[k] = fr.f * fmaf(-fr.ut[6], rx[k], fmaf(-fr.ut[7], ry[k], fmaf(-fr.ut[8], rz[k], z[k] - fr.c[2])));
     }
   }
 };
@@ -603,11 +610,14 @@ struct RmsdCV : cvp_cv {
   int use_fused = 1;    // option "fused": one-read persistent kernel for the streaming fast path
   int fused_lag = 3;    // option "fused_lag": rounds between the sums and the gradient of a frame
   int fused_slice = 0;  // option "fused_slice": atoms per sub-slice (0 = chosen by the planner)
+  int fused_slots = 0;  // option "fused_slots": auxiliary-data slots per CTA (0 = planner)
+  int fused_hints = 3;  // option "fused_hints": L2 eviction hints (see FusedGeom::l2_hints)
   int fast_first = 0, fast_nslice = 0;
   std::vector<float> ref_f32;
   std::vector<int32_t> fast_seg_slice_offsets;
   std::vector<double> fast_gy;
-  DeviceBuffer d_ref_f32, d_fast_seg_slice_offsets, d_fast_gy;
+  DeviceBuffer d_ref_f32, d_ref_perm, d_fast_seg_slice_offsets, d_fast_gy;
+  std::vector<double> ref_perm;  // ref_f32 as doubles in the layout of fused_permute_doubles()
   int num_groups = 0, nseg = 0, nslice = 0;
   int64_t num_entries = 0;
   CombineParams cp{};
@@ -626,7 +636,7 @@ struct RmsdCV : cvp_cv {
     for (DeviceBuffer* buf :
          {&d_entry_atom, &d_entry_group, &d_entry_seg, &d_ref, &d_slices, &d_group_seg_offsets,
           &d_seg_slice_offsets, &d_seg_size, &d_group_size, &d_group_gy, &d_active,
-          &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_fast_seg_slice_offsets, &d_fast_gy})
+          &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_ref_perm, &d_fast_seg_slice_offsets, &d_fast_gy})
       buf->release();
   }
   int upload() override {
@@ -647,6 +657,7 @@ struct RmsdCV : cvp_cv {
     CVP_UP(d_atom_entry_offsets, atom_entry_offsets);
     CVP_UP(d_atom_entries, atom_entries);
     CVP_UP(d_ref_f32, ref_f32);
+    CVP_UP(d_ref_perm, ref_perm);
     CVP_UP(d_fast_seg_slice_offsets, fast_seg_slice_offsets);
     CVP_UP(d_fast_gy, fast_gy);
 #undef CVP_UP
@@ -672,6 +683,14 @@ struct RmsdCV : cvp_cv {
     }
     if (key == "fused_slice") {
       std::swap(fused_slice, value);
+      return value;
+    }
+    if (key == "fused_slots") {
+      std::swap(fused_slots, value);
+      return value;
+    }
+    if (key == "fused_hints") {
+      std::swap(fused_hints, value);
       return value;
     }
     return cvp_cv::set_option(name, value);
@@ -700,7 +719,7 @@ struct RmsdCV : cvp_cv {
     FusedGeom geom;
     if (use_fast && use_fused && cp.mode == CVP_COMBINE_IDENTITY && B >= 64 &&
         FusedLaunch<RmsdFusedPolicy>::plan((int)num_entries, N, fast_first, B, grad != nullptr,
-                                           fused_lag, fused_slice, sm_count(), &geom)) {
+                                           fused_lag, fused_slice, fused_slots, fused_hints, sm_count(), &geom)) {
       RmsdFusedPolicy::Params params;
       params.gy = fast_gy[0];
       params.n = (int)num_entries;
@@ -708,8 +727,8 @@ struct RmsdCV : cvp_cv {
         CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
       timer.begin("rmsd_fused", st);
       int status = FusedLaunch<RmsdFusedPolicy>::launch(
-          reinterpret_cast<const float*>(pos), static_cast<const float*>(d_ref_f32.ptr), geom,
-          sm_count(), params, ws, reinterpret_cast<float*>(value), reinterpret_cast<float*>(grad),
+          reinterpret_cast<const float*>(pos), static_cast<const float*>(d_ref_f32.ptr),
+          static_cast<const double*>(d_ref_perm.ptr), geom, sm_count(), params, ws, reinterpret_cast<float*>(value), reinterpret_cast<float*>(grad),
           accumulate, st);
       timer.end(st);
       return status;
@@ -906,6 +925,7 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
         gy += (double)cv->ref_f32[k] * (double)cv->ref_f32[k];
       }
       cv->fast_gy.assign(1, gy);
+      cv->ref_perm = fused_permute_doubles(cv->ref_f32.data(), (size_t)E);
       cv->fast_seg_slice_offsets = {0, cv->fast_nslice};
     }
   }

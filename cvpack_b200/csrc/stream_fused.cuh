@@ -12,16 +12,20 @@
 //   * iteration t of a warp: SUM(frame t*RR + r), then GRAD(frame (t-L)*RR + r): the lag is L rounds
 //     = L*RR frames = L * (about 12 MB of coordinates), whatever the size of the group;
 //   * every warp is autonomous: its own TMA ring (cp.async.bulk global->shared, one mbarrier per
-//     stage, refilled by lane 0 as soon as the lanes have copied a chunk to registers), its own
-//     resident sub-slice of the per-atom auxiliary data (centred reference / weights) in shared
-//     memory, its own output staging for TMA bulk stores (or bulk reduce-add when accumulating).
-//     There is no block-wide barrier anywhere, and the loads in flight do not depend on registers
-//     or occupancy.
+//     stage, refilled by lane 0 as soon as the lanes have copied a chunk to registers) and its own
+//     output staging for TMA bulk stores (or bulk reduce-add when accumulating).  The sub-slice of
+//     the per-atom auxiliary data (centred reference / weights) stays resident in shared memory,
+//     one copy per *slot* shared by the warps of the CTA that work on the same sub-slice (for
+//     different frames).  There is no block-wide barrier after the set-up, and the loads in flight
+//     do not depend on registers or occupancy.
 // Dependencies inside the launch:
-//   * a SUM item ends with a release-add on the frame's counter.  One extra *solver warp* per CTA
-//     owns the frames f = cta, cta + #CTAs, ...: it waits for the counter to reach SS, adds the
-//     sub-slice partials in slice order (deterministic), runs the per-frame solve in one lane and
-//     publishes the frame constants with a release flag.  (Letting the last streaming warp solve
+//   * a SUM item ends by writing its partial sums as tagged records: every double travels as
+//     {lo, tag, hi, tag} (one 16-byte store; each 8-byte half carries the round's tag, the way
+//     NCCL's LL protocol does), so the streaming warps need neither a fence nor a counter.  One
+//     extra *solver warp* per CTA owns the frames f = cta, cta + #CTAs, ...: it reads the records
+//     of the frame's SS sub-slices, re-reading those whose tags have not arrived, adds them in
+//     slice order (deterministic), runs the per-frame solve in one lane and publishes the frame
+//     constants with a release flag.  (Letting the last streaming warp solve
 //     puts the solve on the critical path of that warp's frame class: it is late for the next
 //     frame, hence last again, and ends up solving every frame of the class serially.)
 //   * GRAD(f) needs that flag.  SUM items never wait and the schedule is static, so the flag a warp
@@ -37,10 +41,10 @@
 
 namespace cvp {
 
-constexpr int FUSED_STAGES = 4;         // chunks in flight per warp
-constexpr int FUSED_CHUNK_ATOMS = 128;  // 4 atoms (3 x float4) per lane
+constexpr int FUSED_STAGES = 2;         // ring stages per warp (refilled right after the LDS)
+constexpr int FUSED_CHUNK_ATOMS = 256;  // 2 x 4 atoms (2 x 3 float4) per lane
 constexpr int FUSED_CHUNK_BYTES = FUSED_CHUNK_ATOMS * 12;
-constexpr int FUSED_MAX_WARPS = 16;
+constexpr int FUSED_MAX_WARPS = 15;  // streaming warps; with the solver warp 16 warps = 128 registers
 constexpr int FUSED_SMEM_LIMIT = 227 * 1024;
 constexpr int FUSED_SCRATCH_ROW = 33;  // doubles per row of the warp reduction scratch (padded)
 
@@ -61,6 +65,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t policy;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
   return policy;
 }
 __device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src,
@@ -108,11 +117,47 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_v4(uint4* p, const uint4& v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Layout of the double-precision auxiliary data (Policy::AUXD == 3): blocks of 128 atoms = 32
+// groups of 4 atoms = 6 double2 per group; piece j of group l of a block sits at double2 index
+// j * 32 + l, so that a warp reads one piece with a conflict-free LDS.128.  The array is padded
+// with zeros to a whole number of blocks.
+inline std::vector<double> fused_permute_doubles(const float* values, size_t atoms) {
+  const size_t blocks = (atoms + 127) / 128;
+  std::vector<double> out(blocks * 128 * 3, 0.0);
+  for (size_t a = 0; a < atoms; ++a)
+    for (int d = 0; d < 3; ++d) {
+      const size_t block = a / 128, group = (a % 128) / 4, k = (a % 4) * 3 + d;  // k in 0..11
+      out[block * 384 + ((k / 2) * 32 + group) * 2 + (k % 2)] = (double)values[a * 3 + d];
+    }
+  return out;
 }
 
 // Geometry of a launch (host-chosen, see FusedLaunch::plan).
@@ -124,58 +169,108 @@ struct FusedGeom {
   int SS, RR;          // sub-slices per frame, frames per round
   int L;               // lag between the sums and the gradient of a frame, in rounds
   int T;               // rounds = ceil(B / RR)
-  int warps_per_cta;
-  int per_warp_bytes;  // shared memory per warp
+  int warps_per_cta;   // streaming warps (one more warp per CTA solves)
+  int slots;           // auxiliary-data slots per CTA; warps_per_cta / slots warps share one
+  int K;               // frame classes per slot column: slot g -> sub-slice g % SS, class g / SS < K
   int ring_rounds;     // rounds of partial sums kept (ring) -- T when there is no gradient
+  int l2_hints;        // bit 0: evict_last for the first read, bit 1: evict_first for second read
+                       // and stores
 };
 
 // Policy:
 //   static constexpr int NS                    number of double sums per frame (<= 16)
 //   static constexpr int AUX                   floats of auxiliary data per atom (0, 1 or 3)
+//   static constexpr int AUXD                  doubles of auxiliary data per atom for the sums (0 or
+//                                              3): the same values, pre-converted, in the
+//                                              conflict-free layout of fused_permute_doubles()
 //   struct Params                              per-launch constants
 //   struct Frame                               per-frame constants of the gradient; 64 bytes
-//   accumulate(params, aux, x, y, z, v)        add 4 atoms to the sums; aux = this lane's 4*AUX
-//                                              floats in shared memory
+//   accumulate(params, aux, auxd, x, y, z, v)  add 4 atoms to the sums; aux = this lane's 4*AUX
+//                                              floats in shared memory, auxd = its first double2
+//                                              (the others follow at strides of 32 double2)
 //   complete(params, sums, frame*, value*, accumulate)   one lane, NOT inlined: solve from the
 //                                              frame's sums, fill Frame, write the value
 //   gradient(params, frame, aux, x, y, z, gx, gy, gz)
 template <typename Policy>
+struct FusedLayout {
+  static constexpr int NS = Policy::NS;
+  static constexpr int SCRATCH_BYTES = (NS * FUSED_SCRATCH_ROW * 8 + 15) / 16 * 16;
+  static constexpr int OUT_BYTES =
+      2 * FUSED_CHUNK_BYTES > SCRATCH_BYTES ? 2 * FUSED_CHUNK_BYTES : SCRATCH_BYTES;
+  static constexpr int RING_BYTES = FUSED_STAGES * FUSED_CHUNK_BYTES;
+  static constexpr int WARP_BYTES = (RING_BYTES + OUT_BYTES + FUSED_STAGES * 8 + 127) / 128 * 128;
+  static int slot_bytes(int sub) {
+    return (sub * (Policy::AUX * 4 + Policy::AUXD * 8) + 127) / 128 * 128;
+  }
+};
+
+template <typename Policy>
 __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
     stream_fused_kernel(const float* __restrict__ pos, const float* __restrict__ aux_global,
-                        FusedGeom geom, typename Policy::Params params, int* __restrict__ done,
-                        int* __restrict__ ready, double* __restrict__ partials,
+                        const double* __restrict__ auxd_global, FusedGeom geom, typename Policy::Params params,
+                        int* __restrict__ ready, uint4* __restrict__ partials,
                         typename Policy::Frame* __restrict__ frames, float* __restrict__ value,
                         float* __restrict__ grad, int accumulate) {
+  using Layout = FusedLayout<Policy>;
   constexpr int NS = Policy::NS;
   constexpr int AUX = Policy::AUX;
-  constexpr int NST = FUSED_STAGES;
+  constexpr int AUXD = Policy::AUXD;
+  constexpr int CH = FUSED_CHUNK_BYTES;
+  static_assert(FUSED_STAGES == 2, "the ring logic below assumes two stages");
   static_assert(sizeof(typename Policy::Frame) == 64, "Frame must be 64 bytes");
   static_assert(NS <= 16, "at most 16 sums");
   extern __shared__ __align__(128) unsigned char fused_smem[];
+  __shared__ uint64_t s_aux_bar[FUSED_MAX_WARPS];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * geom.warps_per_cta + warp;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // (warp-uniform for the compiler)
+  const int lane = threadIdx.x & 31;
   const int SS = geom.SS, RR = geom.RR, L = geom.L, T = geom.T;
   const int64_t B = geom.num_frames;
   const bool has_grad = grad != nullptr;
+  const bool use_ring = geom.ring_rounds < T;  // partial records: ring of rounds, else one per frame
+  const int wpc = geom.warps_per_cta;
+  const int wps = wpc / geom.slots;  // warps per slot
+  const int slot_bytes = (geom.sub * (AUX * 4 + AUXD * 8) + 127) / 128 * 128;
 
-  if (warp == geom.warps_per_cta) {
+  // ---- set-up: barriers, auxiliary data of this CTA's slots -------------------------------------
+  const uint64_t pol_keep = (geom.l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
+  const uint64_t pol_stream =
+      (geom.l2_hints & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
+  unsigned char* warp_base = fused_smem + (size_t)geom.slots * slot_bytes + (size_t)warp * Layout::WARP_BYTES;
+  unsigned char* s_ring = warp_base;
+  unsigned char* s_out = warp_base + Layout::RING_BYTES;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + Layout::OUT_BYTES);
+  if (warp < wpc && lane == 0) {
+    mbar_init(s_bar, 1);
+    mbar_init(s_bar + 1, 1);
+    if (warp < geom.slots) mbar_init(s_aux_bar + warp, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();  // the only block-wide barrier: the aux barriers are shared between warps
+
+  if (warp == wpc) {
     // ---- solver warp: frames blockIdx.x, blockIdx.x + gridDim.x, ... ------------------------------
     for (int64_t frame = blockIdx.x; frame < B; frame += gridDim.x) {
-      if (lane == 0) {
-        while (ld_acquire_gpu(done + frame) < SS) __nanosleep(100);
-      }
-      __syncwarp();
-      __threadfence();
-      const int64_t slot =
-          has_grad ? (int64_t)((frame / RR) % geom.ring_rounds) * RR + frame % RR : frame;
+      const int round = (int)(frame / RR);
+      const uint32_t tag = (uint32_t)round + 1u;
+      const int64_t slot = use_ring ? (int64_t)(round % geom.ring_rounds) * RR + frame % RR : frame;
       double sums[NS];
 #pragma unroll
       for (int k = 0; k < NS; ++k) sums[k] = 0.0;
-      const double* in = partials + slot * SS * NS;
+      const uint4* in = partials + slot * SS * NS;
       for (int q = lane; q < SS; q += 32) {
+        const uint4* rec = in + (size_t)q * NS;
+        uint4 v[NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) sums[k] += __ldcg(in + (size_t)q * NS + k);
+        for (int k = 0; k < NS; ++k) v[k] = ld_relaxed_gpu_v4(rec + k);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+          while (v[k].y != tag || v[k].w != tag) {
+            __nanosleep(100);
+            v[k] = ld_relaxed_gpu_v4(rec + k);
+          }
+          sums[k] += __hiloint2double((int)v[k].z, (int)v[k].x);
+        }
       }
 #pragma unroll
       for (int k = 0; k < NS; ++k) sums[k] = warp_sum(sums[k]);
@@ -188,102 +283,95 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
     }
     return;
   }
-  if (gw >= SS * RR) return;  // (no block-wide barrier anywhere)
-  const int s = gw % SS, r = gw / SS;
-  if (r >= B) return;
 
-  // this warp's sub-slice
+  // ---- streaming warp (s, r) ----------------------------------------------------------------------
+  const int my_slot = warp / wps;
+  const int gslot = blockIdx.x * geom.slots + my_slot;
+  const bool working = gslot < SS * geom.K;
+  const int s = gslot % SS;
+  const int r = (gslot / SS) * wps + (warp - my_slot * wps);
   const int a0 = s * geom.sub;
-  const int sub_n = min(geom.sub, geom.n - a0);  // atoms (multiple of 4)
-  const int ng = sub_n >> 2;                     // groups of 4 atoms
-  const int nch = (ng + 31) >> 5;                // chunks per item
-
-  // shared memory of this warp
-  unsigned char* base = fused_smem + (size_t)warp * geom.per_warp_bytes;
-  float* s_aux = reinterpret_cast<float*>(base);
-  unsigned char* s_ring = base + (size_t)geom.sub * AUX * 4;
-  constexpr int OUT_BYTES =
-      (2 * FUSED_CHUNK_BYTES > NS * FUSED_SCRATCH_ROW * 8 ? 2 * FUSED_CHUNK_BYTES
-                                                          : NS * FUSED_SCRATCH_ROW * 8 + 15) /
-      16 * 16;
-  unsigned char* s_out = s_ring + NST * FUSED_CHUNK_BYTES;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + OUT_BYTES);  // NST ring barriers + 1 (aux)
-
-  const uint64_t pol_keep = l2_policy_evict_last();
-  const uint64_t pol_stream = l2_policy_evict_first();
-
-  if (lane == 0) {
-    for (int k = 0; k <= NST; ++k) mbar_init(s_bar + k, 1);
-    mbar_fence_init();
-    if (AUX > 0) {
-      const uint32_t bytes = (uint32_t)sub_n * AUX * 4;
-      mbar_expect_tx(s_bar + NST, bytes);
-      tma_load_1d_hint(s_aux, aux_global + (size_t)a0 * AUX, bytes, s_bar + NST, pol_keep);
-    }
+  const int sub_n = min(geom.sub, geom.n - a0);  // atoms of this sub-slice (multiple of 4)
+  // slot: [doubles, blocks of 128 atoms in the permuted layout][floats]
+  double* s_auxd = reinterpret_cast<double*>(fused_smem + (size_t)my_slot * slot_bytes);
+  float* s_aux = reinterpret_cast<float*>(s_auxd + (size_t)geom.sub * AUXD);
+  if (AUX + AUXD > 0 && working && warp == my_slot * wps && lane == 0) {
+    const uint32_t bytes = (uint32_t)sub_n * AUX * 4;
+    const uint32_t bytes_d = (uint32_t)((sub_n + 127) / 128 * 128) * AUXD * 8;
+    mbar_expect_tx(s_aux_bar + my_slot, bytes + bytes_d);
+    if (AUX > 0)
+      tma_load_1d_hint(s_aux, aux_global + (size_t)a0 * AUX, bytes, s_aux_bar + my_slot,
+                       l2_policy_evict_last());
+    if (AUXD > 0)
+      tma_load_1d_hint(s_auxd, auxd_global + (size_t)a0 * AUXD, bytes_d, s_aux_bar + my_slot,
+                       l2_policy_evict_last());
   }
-  __syncwarp();
+  if (!working || r >= B) return;
 
-  // ---- producer cursor (uniform across the warp; lane 0 issues) ----------------------------------
+  const int ng = sub_n >> 2;         // groups of 4 atoms
+  const int nch = (ng + 63) >> 6;    // chunks per item
+  const uint32_t last_bytes = (uint32_t)(ng - ((nch - 1) << 6)) * 48u;
+  const int64_t frame_stride = geom.num_atoms * 3;  // floats
+  const float* slice_base = pos + ((int64_t)geom.first_atom + a0) * 3;
+
+  // producer (lane 0 keeps the state): chunks of the item sequence SUM(0) [GRAD(0-L)] SUM(1) ...
   auto job_valid = [&](int t, int half) -> bool {
     if (half == 0) return t < T && (int64_t)t * RR + r < B;
     return has_grad && t >= L && (int64_t)(t - L) * RR + r < B;
   };
   const int t_end = T + (has_grad ? L : 0);
-  int p_t = 0, p_half = 0, p_c = 0;  // (0, 0) is valid because r < B
+  int p_t = 0, p_half = 0, p_left = nch, p_stage = 0;
   bool p_done = false;
-  uint32_t prod_q = 0, cons_q = 0;
-  const float* slice_base = pos + ((int64_t)geom.first_atom + a0) * 3;
-  const int64_t frame_stride = geom.num_atoms * 3;
-
-  auto produce_one = [&]() {
+  const float* p_ptr = slice_base + (int64_t)r * frame_stride;
+  auto produce = [&]() {  // all lanes keep the (uniform) state, one lane issues
     if (p_done) return;
-    const int64_t frame = (int64_t)(p_half == 0 ? p_t : p_t - L) * RR + r;
-    const int first_group = p_c << 5;
-    const uint32_t bytes = (uint32_t)min(32, ng - first_group) * 48u;
-    const int stage = prod_q % NST;
-    if (lane == 0) {
-      mbar_expect_tx(s_bar + stage, bytes);
-      tma_load_1d_hint(s_ring + stage * FUSED_CHUNK_BYTES,
-                       slice_base + frame * frame_stride + (int64_t)first_group * 12, bytes,
-                       s_bar + stage, (p_half == 0 && has_grad) ? pol_keep : pol_stream);
+    const uint32_t bytes = p_left == 1 ? last_bytes : (uint32_t)CH;
+    if (elect_one()) {
+      mbar_expect_tx(s_bar + p_stage, bytes);
+      tma_load_1d_hint(s_ring + p_stage * CH, p_ptr, bytes, s_bar + p_stage,
+                       p_half == 0 && has_grad ? pol_keep : pol_stream);
     }
-    ++prod_q;
-    if (++p_c == nch) {
-      p_c = 0;
+    p_stage ^= 1;
+    p_ptr += CH / 4;
+    if (--p_left == 0) {
       for (;;) {
-        if (p_half == 0) {
-          p_half = 1;
-        } else {
-          p_half = 0;
-          ++p_t;
-        }
+        p_t += p_half;
+        p_half ^= 1;
         if (p_t >= t_end) {
           p_done = true;
-          break;
+          return;
         }
         if (job_valid(p_t, p_half)) break;
       }
+      p_left = nch;
+      p_ptr = slice_base + ((int64_t)(p_half == 0 ? p_t : p_t - L) * RR + r) * frame_stride;
     }
   };
-  for (int k = 0; k < NST; ++k) produce_one();
-  if (AUX > 0) mbar_wait(s_bar + NST, 0);
+  produce();
+  produce();
+  if (AUX + AUXD > 0) mbar_wait(s_aux_bar + my_slot, 0);
+
+  uint32_t cons_q = 0;     // chunks consumed: stage = q & 1, parity = (q >> 1) & 1
+  int out_buf = 0;
+  const float4* lane_ring = reinterpret_cast<const float4*>(s_ring) + 3 * lane;
+  const float* lane_aux = s_aux + lane * 4 * AUX;
+  const double2* lane_auxd = reinterpret_cast<const double2*>(s_auxd) + lane;
 
   // frame constants of the next GRAD item, fetched early
   int pre_flag = 0;
   float4 pre[4];
-  auto prefetch_frame = [&](int64_t frame) {
-    pre_flag = ld_relaxed_gpu(ready + frame);
-    // slot 0 is a dummy: the address depends on the flag, so the loads cannot pass it
-    const float4* src = reinterpret_cast<const float4*>(frames + (pre_flag != 0 ? frame + 1 : 0));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) pre[k] = __ldcg(src + k);
-  };
 
-  int out_buf = 0;
   for (int t = 0; t < t_end; ++t) {
     const bool grad_valid = job_valid(t, 1);
     const int64_t grad_frame = (int64_t)(t - L) * RR + r;
-    if (grad_valid) prefetch_frame(grad_frame);
+    if (grad_valid) {
+      pre_flag = ld_relaxed_gpu(ready + grad_frame);
+      // slot 0 is a dummy: the address depends on the flag, so the loads cannot pass it
+      const float4* src =
+          reinterpret_cast<const float4*>(frames + (pre_flag != 0 ? grad_frame + 1 : 0));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pre[k] = __ldcg(src + k);
+    }
 
     if (job_valid(t, 0)) {
       // ---- SUM -----------------------------------------------------------------------------------
@@ -291,27 +379,26 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
       double v[NS];
 #pragma unroll
       for (int k = 0; k < NS; ++k) v[k] = 0.0;
-      for (int c = 0; c < nch; ++c) {
-        const int stage = cons_q % NST;
-        mbar_wait(s_bar + stage, (cons_q / NST) & 1);
-        const int g = (c << 5) + lane;
-        const bool active = g < ng;
-        const float4* px =
-            reinterpret_cast<const float4*>(s_ring + stage * FUSED_CHUNK_BYTES) + 3 * lane;
-        float4 x0, x1, x2;
-        if (active) {
-          x0 = px[0];
-          x1 = px[1];
-          x2 = px[2];
+      int left = ng;
+      const float* aux = lane_aux;
+      const double2* auxd = lane_auxd;
+      for (int c = 0; c < nch; ++c, left -= 64, aux += 64 * 4 * AUX, auxd += 64 * AUXD * 2) {
+        const int stage = cons_q & 1;
+        mbar_wait(s_bar + stage, (cons_q >> 1) & 1);
+        ++cons_q;
+        const float4* px = lane_ring + stage * (CH / 16);
+        if (lane < left) {
+          float x[4], y[4], z[4];
+          fused_unpack4(px[0], px[1], px[2], x, y, z);
+          Policy::accumulate(params, aux, auxd, x, y, z, v);
+        }
+        if (lane + 32 < left) {
+          float x[4], y[4], z[4];
+          fused_unpack4(px[96], px[97], px[98], x, y, z);
+          Policy::accumulate(params, aux + 32 * 4 * AUX, auxd + 32 * AUXD * 2, x, y, z, v);
         }
         __syncwarp();
-        ++cons_q;
-        produce_one();
-        if (active) {
-          float x[4], y[4], z[4];
-          fused_unpack4(x0, x1, x2, x, y, z);
-          Policy::accumulate(params, s_aux + (size_t)g * 4 * AUX, x, y, z, v);
-        }
+        produce();
       }
       // warp reduction through shared memory (the output staging is idle: drain its readers)
       if (lane == 0) tma_wait_group_read<0>();
@@ -329,21 +416,25 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
           for (int i = 0; i < 16; ++i) acc += row[i];
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        const int64_t slot = has_grad ? (int64_t)(t % geom.ring_rounds) * RR + r : frame;
-        if (k2 < NS && h == 0) __stcg(partials + (slot * SS + s) * NS + k2, acc);
+        const int64_t slot = use_ring ? (int64_t)(t % geom.ring_rounds) * RR + r : frame;
+        if (k2 < NS && h == 0) {
+          const uint32_t tag = (uint32_t)t + 1u;
+          st_relaxed_gpu_v4(partials + (slot * SS + s) * NS + k2,
+                            make_uint4((uint32_t)__double2loint(acc), tag,
+                                       (uint32_t)__double2hiint(acc), tag));
+        }
       }
-      __syncwarp();
-      if (lane == 0) red_release_add(done + frame, 1);
+      __syncwarp();  // (the scratch is the output staging of the next GRAD item)
     }
 
     if (grad_valid) {
       // ---- GRAD ----------------------------------------------------------------------------------
       if (!__all_sync(0xffffffffu, pre_flag != 0)) {
         if (lane == 0) {
-          while (ld_acquire_gpu(ready + grad_frame) == 0) __nanosleep(200);
+          while (ld_relaxed_gpu(ready + grad_frame) == 0) __nanosleep(256);
         }
         __syncwarp();
-        __threadfence();
+        (void)ld_acquire_gpu(ready + grad_frame);
         const float4* src = reinterpret_cast<const float4*>(frames + grad_frame + 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) pre[k] = __ldcg(src + k);
@@ -354,44 +445,43 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 #pragma unroll
         for (int k = 0; k < 4; ++k) dst[k] = pre[k];
       }
-      float* gbase = grad + grad_frame * frame_stride + ((int64_t)geom.first_atom + a0) * 3;
-      for (int c = 0; c < nch; ++c) {
-        const int stage = cons_q % NST;
-        mbar_wait(s_bar + stage, (cons_q / NST) & 1);
-        const int g = (c << 5) + lane;
-        const bool active = g < ng;
-        const float4* px =
-            reinterpret_cast<const float4*>(s_ring + stage * FUSED_CHUNK_BYTES) + 3 * lane;
-        float4 x0, x1, x2;
-        if (active) {
-          x0 = px[0];
-          x1 = px[1];
-          x2 = px[2];
-        }
+      float* gdst = grad + grad_frame * frame_stride + ((int64_t)geom.first_atom + a0) * 3;
+      int left = ng;
+      const float* aux = lane_aux;
+      for (int c = 0; c < nch; ++c, left -= 64, aux += 64 * 4 * AUX, gdst += CH / 4) {
+        const int stage = cons_q & 1;
+        mbar_wait(s_bar + stage, (cons_q >> 1) & 1);
+        ++cons_q;
+        const float4* px = lane_ring + stage * (CH / 16);
         // the staging buffer written two chunks ago must have been read by its bulk store
         if (lane == 0) tma_wait_group_read<1>();
         __syncwarp();
-        ++cons_q;
-        produce_one();
-        float4* po = reinterpret_cast<float4*>(s_out + out_buf * FUSED_CHUNK_BYTES) + 3 * lane;
-        if (active) {
+        float4* po = reinterpret_cast<float4*>(s_out + out_buf * CH) + 3 * lane;
+        if (lane < left) {
           float x[4], y[4], z[4], gx[4], gy[4], gz[4];
-          fused_unpack4(x0, x1, x2, x, y, z);
-          Policy::gradient(params, fr, s_aux + (size_t)g * 4 * AUX, x, y, z, gx, gy, gz);
+          fused_unpack4(px[0], px[1], px[2], x, y, z);
+          Policy::gradient(params, fr, aux, x, y, z, gx, gy, gz);
           po[0] = make_float4(gx[0], gy[0], gz[0], gx[1]);
           po[1] = make_float4(gy[1], gz[1], gx[2], gy[2]);
           po[2] = make_float4(gz[2], gx[3], gy[3], gz[3]);
         }
+        if (lane + 32 < left) {
+          float x[4], y[4], z[4], gx[4], gy[4], gz[4];
+          fused_unpack4(px[96], px[97], px[98], x, y, z);
+          Policy::gradient(params, fr, aux + 32 * 4 * AUX, x, y, z, gx, gy, gz);
+          po[96] = make_float4(gx[0], gy[0], gz[0], gx[1]);
+          po[97] = make_float4(gy[1], gz[1], gx[2], gy[2]);
+          po[98] = make_float4(gz[2], gx[3], gy[3], gz[3]);
+        }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          const int first_group = c << 5;
-          const uint32_t bytes = (uint32_t)min(32, ng - first_group) * 48u;
-          float* dst = gbase + (int64_t)first_group * 12;
+        produce();
+        if (elect_one()) {
+          const uint32_t bytes = c == nch - 1 ? last_bytes : (uint32_t)CH;
           if (accumulate)
-            tma_reduce_add_f32_1d(dst, s_out + out_buf * FUSED_CHUNK_BYTES, bytes);
+            tma_reduce_add_f32_1d(gdst, s_out + out_buf * CH, bytes);
           else
-            tma_store_1d(dst, s_out + out_buf * FUSED_CHUNK_BYTES, bytes, pol_stream);
+            tma_store_1d(gdst, s_out + out_buf * CH, bytes, pol_stream);
           tma_commit_group();
         }
         out_buf ^= 1;
@@ -404,55 +494,59 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 // Host helper: geometry, workspace layout and launch.
 template <typename Policy>
 struct FusedLaunch {
-  static constexpr int out_bytes() {
-    return (2 * FUSED_CHUNK_BYTES > Policy::NS * FUSED_SCRATCH_ROW * 8
-                ? 2 * FUSED_CHUNK_BYTES
-                : Policy::NS * FUSED_SCRATCH_ROW * 8 + 15) /
-           16 * 16;
-  }
-  static int per_warp_bytes(int sub) {
-    const int bytes = sub * Policy::AUX * 4 + FUSED_STAGES * FUSED_CHUNK_BYTES + out_bytes() +
-                      (FUSED_STAGES + 1) * 8;
-    return (bytes + 127) / 128 * 128;
-  }
-  // workspace: done[B], ready[B], frames[B + 1], partials[B * SS_max * NS]; SS_max for sub = 128
+  using Layout = FusedLayout<Policy>;
+  // workspace: ready[B], frames[B + 1], partial records[B * SS_max * NS]; SS_max for the smallest
+  // sub-slice
   static size_t workspace_per_frame(int n) {
     const size_t ss_max = (size_t)div_up(n, FUSED_CHUNK_ATOMS);
-    return ss_max * Policy::NS * sizeof(double) + sizeof(typename Policy::Frame) + 2 * sizeof(int) +
+    return ss_max * Policy::NS * sizeof(uint4) + sizeof(typename Policy::Frame) + 2 * sizeof(int) +
            16;
   }
   static size_t workspace_fixed() { return 8 * 256 + sizeof(typename Policy::Frame); }
 
-  // Chooses the sub-slice size: fills the resident warps (SS * RR of SMs * warps_per_cta) with as
-  // little rounding loss as possible; larger sub-slices (fewer reductions) win ties.  Returns false
-  // when the problem does not fit the scheme (group too small or too large, too few frames).
+  // Chooses the sub-slice size and how many warps share one auxiliary-data slot: fills the
+  // resident warps with as little rounding loss as possible; larger sub-slices (fewer per-item
+  // reductions) win ties.  Returns false when the problem does not fit the scheme (group too small
+  // or too large, not 16-byte aligned).
   static bool plan(int n, int64_t num_atoms, int first_atom, int64_t num_frames, bool has_grad,
-                   int lag_rounds, int sub_option, int sms, FusedGeom* geom) {
-    if (n < 4 * FUSED_CHUNK_ATOMS || n % 4 != 0 || first_atom % 4 != 0 || num_atoms % 4 != 0)
+                   int lag_rounds, int sub_option, int slots_option, int l2_hints, int sms,
+                   FusedGeom* geom) {
+    if (n < 2 * FUSED_CHUNK_ATOMS || n % 4 != 0 || first_atom % 4 != 0 || num_atoms % 4 != 0)
       return false;
     double best = 0.0;
     FusedGeom g{};
     for (int sub = FUSED_CHUNK_ATOMS; sub <= 8 * FUSED_CHUNK_ATOMS; sub += FUSED_CHUNK_ATOMS) {
       if (sub_option > 0 && sub != sub_option) continue;
-      const int pwb = per_warp_bytes(sub);
-      const int wpc = std::min(FUSED_MAX_WARPS, (FUSED_SMEM_LIMIT - 1024) / pwb);  // + the solver warp
-      if (wpc < 1) continue;
-      const int64_t W = (int64_t)sms * wpc;
       const int64_t SS = div_up(n, sub);
-      if (SS > W) continue;
-      const int64_t RR = std::min<int64_t>(W / SS, num_frames);
-      // fraction of the machine's warp slots doing useful work, discounted for the per-item
-      // reduction (about 60 instructions against 25 per atom and lane)
-      const double fill = (double)(SS * RR) / (double)W * (double)n / (double)(SS * sub);
-      const double overhead = 1.0 / (1.0 + 60.0 / (25.0 * sub / 32.0));
-      const double score = fill * overhead * (double)wpc / FUSED_MAX_WARPS;
-      if (score > best) {
-        best = score;
-        g.sub = sub;
-        g.SS = (int)SS;
-        g.RR = (int)RR;
-        g.warps_per_cta = wpc;
-        g.per_warp_bytes = pwb;
+      for (int slots = 1; slots <= FUSED_MAX_WARPS; ++slots) {
+        if (slots_option > 0 && slots != slots_option) continue;
+        if (Policy::AUX == 0 && slots_option <= 0 && slots != FUSED_MAX_WARPS) continue;
+        const int budget = FUSED_SMEM_LIMIT - 1024 - slots * Layout::slot_bytes(sub);
+        if (budget <= 0) continue;
+        int wpc = std::min(FUSED_MAX_WARPS, budget / Layout::WARP_BYTES);
+        wpc = wpc / slots * slots;
+        if (wpc < slots) continue;
+        const int wps = wpc / slots;
+        const int64_t total_slots = (int64_t)sms * slots;
+        const int64_t K = std::min<int64_t>(total_slots / SS, div_up(num_frames, wps));
+        if (K < 1) continue;
+        // fraction of the machine's warp slots doing useful work, discounted for the per-item
+        // reduction (about 80 instructions against 25 per atom and lane) and for thin occupancy
+        const double fill = (double)(SS * K) / (double)total_slots * (double)n / (double)(SS * sub);
+        const double overhead = 1.0 / (1.0 + 80.0 / (25.0 * sub / 32.0));
+        // a round (all resident warps, one item each) should stay well inside the L2
+        const double round_mb = (double)(K * wps) * n * 12.0 / (1 << 20);
+        const double l2 = round_mb > 16.0 ? std::sqrt(16.0 / round_mb) : 1.0;
+        const double score = fill * overhead * l2 * std::sqrt((double)wpc / FUSED_MAX_WARPS);
+        if (score > best * 1.0001) {
+          best = score;
+          g.sub = sub;
+          g.SS = (int)SS;
+          g.K = (int)K;
+          g.RR = (int)(K * wps);
+          g.warps_per_cta = wpc;
+          g.slots = slots;
+        }
       }
     }
     if (best == 0.0) return false;
@@ -462,36 +556,42 @@ struct FusedLaunch {
     g.n = n;
     g.T = (int)div_up(num_frames, g.RR);
     g.L = std::max(1, std::min(lag_rounds, g.T));
-    g.ring_rounds = has_grad ? std::min(g.T, g.L + 2) : g.T;
+    g.ring_rounds = has_grad ? std::min(g.T, g.L + 2) : g.T;  // (== T: records indexed by frame)
+    g.l2_hints = l2_hints;
     *geom = g;
     return true;
   }
 
-  static int launch(const float* pos, const float* aux, const FusedGeom& geom, int sms,
+  static int launch(const float* pos, const float* aux, const double* auxd, const FusedGeom& geom,
+                    int sms,
                     const typename Policy::Params& params, void* workspace, float* value,
                     float* grad, bool accumulate, cudaStream_t stream) {
     using Frame = typename Policy::Frame;
     const size_t B = (size_t)geom.num_frames;
     Carver carve(workspace);
-    int* flags = carve.take<int>(2 * B);
+    int* ready = carve.take<int>(B);
     Frame* frames = carve.take<Frame>(B + 1);
-    double* partials = carve.take<double>((size_t)geom.ring_rounds * geom.RR * geom.SS * Policy::NS);
-    CVP_CUDA_CHECK(cudaMemsetAsync(flags, 0, 2 * B * sizeof(int), stream));
-    int* done = flags;
-    int* ready = flags + B;
-    const size_t smem = (size_t)geom.warps_per_cta * geom.per_warp_bytes;
+    const size_t record_frames =
+        geom.ring_rounds < geom.T ? (size_t)geom.ring_rounds * geom.RR : B;  // (ring: < B frames)
+    const size_t records = record_frames * geom.SS * Policy::NS;
+    uint4* partials = carve.take<uint4>(records);
+    CVP_CUDA_CHECK(cudaMemsetAsync(ready, 0, B * sizeof(int), stream));
+    CVP_CUDA_CHECK(cudaMemsetAsync(partials, 0, records * sizeof(uint4), stream));  // tag 0 = empty
+    const size_t smem = (size_t)geom.slots * Layout::slot_bytes(geom.sub) +
+                        (size_t)geom.warps_per_cta * Layout::WARP_BYTES;
     static bool configured = false;
     if (!configured) {
       CVP_CUDA_CHECK(cudaFuncSetAttribute(stream_fused_kernel<Policy>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          FUSED_SMEM_LIMIT));
+                                          FUSED_SMEM_LIMIT - 1024));  // (static: aux barriers)
       configured = true;
     }
-    const int blocks = (int)std::min<int64_t>(sms, div_up((int64_t)geom.SS * geom.RR, geom.warps_per_cta));
+    const int blocks =
+        (int)std::min<int64_t>(sms, div_up((int64_t)geom.SS * geom.K, geom.slots));
     FusedGeom g = geom;
     typename Policy::Params p = params;
     int acc = accumulate ? 1 : 0;
-    void* args[] = {(void*)&pos, (void*)&aux, (void*)&g,      (void*)&p,     (void*)&done, (void*)&ready,
+    void* args[] = {(void*)&pos, (void*)&aux, (void*)&auxd, (void*)&g, (void*)&p, (void*)&ready,
                     (void*)&partials, (void*)&frames, (void*)&value, (void*)&grad, (void*)&acc};
     // cooperative: all CTAs are guaranteed to be co-resident (GRAD items wait for other CTAs)
     CVP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)stream_fused_kernel<Policy>, dim3(blocks),

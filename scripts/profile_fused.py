@@ -12,6 +12,7 @@ ctx = cvpack.BatchContext(system, x, None, device=dev)
 nat = ctx._native_cv(cv)
 nat.set_option("fused_slice", int(sys.argv[3]) if len(sys.argv) > 3 else 0)
 nat.set_option("fused_lag", int(sys.argv[4]) if len(sys.argv) > 4 else 3)
+nat.set_option("fused_slots", int(sys.argv[5]) if len(sys.argv) > 5 else 0)
 value = torch.empty(frames, device=dev); grad = torch.empty_like(x)
 for _ in range(3): ctx.evaluateInto(cv, value, grad)
 torch.cuda.synchronize()

@@ -5,6 +5,8 @@ import bench, cvpack_b200 as cvpack
 which = sys.argv[1] if len(sys.argv) > 1 else "rmsd"
 subs = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 lags = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [3]
+slots_list = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
+hints_list = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [3]
 spec = bench.WORKLOADS[which]
 dev = torch.device("cuda:0")
 x, ref = bench.make_positions(which, spec, spec["frames"], 100, device=dev)
@@ -26,10 +28,15 @@ ms, gbs = run()
 print(f"two-pass: {ms:.3f} ms  {gbs:.0f} GB/s ({gbs/6450.9:.2f})", flush=True)
 v0 = value.clone(); g0 = grad.clone()
 nat.set_option("fused", 1)
-for sub in subs:
-    for lag in lags:
-        nat.set_option("fused_slice", sub); nat.set_option("fused_lag", lag)
+import itertools
+for sub, slots, lag, hints in itertools.product(subs, slots_list, lags, hints_list):
+    nat.set_option("fused_slice", sub); nat.set_option("fused_lag", lag)
+    nat.set_option("fused_slots", slots); nat.set_option("fused_hints", hints)
+    value.zero_(); grad.zero_()
+    try:
         ms, gbs = run()
-        dv = (value - v0).abs().max().item() / v0.abs().max().item()
-        dg = (grad - g0).abs().max().item() / g0.abs().max().item()
-        print(f"sub {sub:5d} lag {lag:3d}: {ms:.3f} ms  {gbs:.0f} GB/s ({gbs/6450.9:.2f})  dv {dv:.1e} dg {dg:.1e}", flush=True)
+    except Exception as exc:
+        print(f"sub {sub:5d} slots {slots:2d} lag {lag:3d} hints {hints}: {exc}"); continue
+    dv = (value - v0).abs().max().item() / v0.abs().max().item()
+    dg = (grad - g0).abs().max().item() / g0.abs().max().item()
+    print(f"sub {sub:5d} slots {slots:2d} lag {lag:3d} hints {hints}: {ms:.3f} ms  {gbs:.0f} GB/s ({gbs/6450.9:.2f})  dv {dv:.1e} dg {dg:.1e}", flush=True)
