@@ -549,7 +549,12 @@ struct FusedLaunch {
         }
       }
     }
-    if (best == 0.0) return false;
+    if (best == 0.0) {
+      if (sub_option > 0 || slots_option > 0)  // the preferred shape does not fit: let the planner pick
+        return plan(n, num_atoms, first_atom, num_frames, has_grad, lag_rounds, 0, 0, l2_hints, sms,
+                    geom);
+      return false;
+    }
     g.num_atoms = num_atoms;
     g.num_frames = num_frames;
     g.first_atom = first_atom;
@@ -596,6 +601,7 @@ struct FusedLaunch {
     // cooperative: all CTAs are guaranteed to be co-resident (GRAD items wait for other CTAs)
     CVP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)stream_fused_kernel<Policy>, dim3(blocks),
                                                dim3((geom.warps_per_cta + 1) * 32), args, smem, stream));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return CVP_OK;
   }
 };
