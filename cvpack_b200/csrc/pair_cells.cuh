@@ -15,6 +15,13 @@
 //                           phase 1: 6-instruction distance test, hits recorded in a per-lane bitmask
 //                           phase 2: lanes walk their own hit bits, so the expensive pair function
 //                                    (rsqrt, step function, switching, gradient) runs on real hits only.
+//   3. symmetric mode     (FP32 contacts with the default step function, disjoint groups, one CTA
+//                         per frame): a single sweep computes both sides of every pair.  The
+//                         gradient of the j atoms is accumulated in shared memory as 32-bit
+//                         fixed-point integers -- integer addition is associative, so the result
+//                         does not depend on the order of the atomics -- with a scale chosen on the
+//                         host such that even `passes`-th of the i atoms pushing one j atom in the
+//                         same direction with the largest possible |dE/dr| cannot overflow.
 // Everything is deterministic: no floating-point atomics, fixed summation order per atom.
 #pragma once
 
@@ -30,6 +37,7 @@ constexpr int CELL_MAX_AXIS = 16;      // cells per axis (<= 4096 cells)
 constexpr int CELL_MAX_CELLS = CELL_MAX_AXIS * CELL_MAX_AXIS * CELL_MAX_AXIS;
 constexpr int CELL_SWEEP_THREADS = 512;
 constexpr int CELL_SMEM_BUDGET = 64 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
+constexpr int CELL_SMEM_BUDGET_SYM = 72 * 1024;  // ... with the j gradient accumulators
 constexpr int TAG_DUMMY = -1;
 
 __host__ __device__ inline int cell_round_up(int n, int m) { return (n + m - 1) / m * m; }
@@ -273,23 +281,32 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
 
 // ---- 2. sweep ------------------------------------------------------------------------------------
 template <typename T>
-__host__ __device__ inline int cell_jchunk() {
-  // j atoms per shared-memory chunk: positions + (2 records per cluster of 8) within the budget
-  const int per_atom = (int)sizeof(typename Vec4<T>::type) * (CELL_CLUSTER + 2) / CELL_CLUSTER;
-  return (CELL_SMEM_BUDGET / per_atom) / CELL_TILE * CELL_TILE;
+__host__ __device__ inline int cell_jchunk(bool sym = false) {
+  // j atoms per shared-memory chunk: positions + (2 records per cluster of 8) within the budget;
+  // the symmetric mode adds 3 integer accumulators per atom and takes a little more room
+  const int per_atom =
+      (int)sizeof(typename Vec4<T>::type) * (CELL_CLUSTER + 2) / CELL_CLUSTER + (sym ? 12 : 0);
+  return ((sym ? CELL_SMEM_BUDGET_SYM : CELL_SMEM_BUDGET) / per_atom) / CELL_TILE * CELL_TILE;
 }
 
 template <typename T>
-__host__ __device__ inline size_t cell_sweep_smem() {
+__host__ __device__ inline size_t cell_sweep_smem(bool sym = false) {
   using T4 = typename Vec4<T>::type;
-  const int jchunk = cell_jchunk<T>();
+  const int jchunk = cell_jchunk<T>(sym);
   const int batch_atoms = (sizeof(T) == 4 ? 16 : 8) * CELL_CLUSTER;
   return sizeof(T4) * ((size_t)jchunk + (size_t)(jchunk / CELL_CLUSTER) * 2 +
-                       (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms + 32));
+                       (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms + 32)) +
+         (sym ? (size_t)jchunk * 3 * sizeof(int) : 0);
+}
+
+// fixed-point conversion of the symmetric mode: round(v * scale) for |v * scale| < 2^22, without
+// leaving the FMA/ALU pipes (the integer sits in the mantissa of v * scale + 1.5 * 2^23)
+__device__ __forceinline__ int sym_fixed(float v, float scale) {
+  return __float_as_int(fmaf(v, scale, 12582912.0f)) - 0x4B400000;
 }
 
 // grid = B * nsplit CTAs; CTA (b, part) owns the i tiles part, part + nsplit, ... (strided by warp).
-template <typename T, int KIND, int PBC, bool OVERLAP, bool GRAD, bool FAST6>
+template <typename T, int KIND, int PBC, bool OVERLAP, bool GRAD, bool FAST6, bool SYM = false>
 __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
     cell_sweep_kernel(const typename Vec4<T>::type* __restrict__ isorted,
                       const typename Vec4<T>::type* __restrict__ jsorted,
@@ -297,7 +314,11 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
                       const typename Vec4<T>::type* __restrict__ atom_params, int ni_pad, int nj_pad,
                       int nsplit, const T* __restrict__ box, int box_mode, PairConsts<T> pc,
                       const T* __restrict__ frame_coef, double* __restrict__ energy_partials,
-                      typename Vec4<T>::type* __restrict__ igrad) {
+                      typename Vec4<T>::type* __restrict__ igrad,
+                      typename Vec4<T>::type* __restrict__ jgrad = nullptr, float sym_scale = 0.f,
+                      int sym_passes = 1) {
+  static_assert(!SYM || (GRAD && !OVERLAP && sizeof(T) == 4 && !PairFn<T, KIND>::HAS_PARAMS),
+                "symmetric mode: FP32 gradients of disjoint groups without per-atom parameters");
   using T4 = typename Vec4<T>::type;
   using Fn = PairFn<T, KIND>;
   constexpr int NCH = Fn::NCH;
@@ -313,11 +334,12 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   constexpr int NW = BATCH_CL * CELL_CLUSTER / 32;
   constexpr int BATCH_ATOMS = BATCH_CL * CELL_CLUSTER;
 
-  const int jchunk = cell_jchunk<T>();
+  const int jchunk = cell_jchunk<T>(SYM);
   T4* jsm = reinterpret_cast<T4*>(sweep_smem);
   T4* bsm = jsm + jchunk;  // cluster boxes of the chunk: (centre, half) pairs
   T4* stage_all = bsm + (jchunk / CELL_CLUSTER) * 2;       // [NWARP][BATCH_ATOMS]
   T4* survivors_all = stage_all + NWARP * BATCH_ATOMS;    // [NWARP][32]
+  int* jacc = reinterpret_cast<int*>(survivors_all + NWARP * 32);  // SYM: [jchunk][3]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.x / nsplit;
@@ -369,10 +391,19 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
                     reinterpret_cast<const char*>(jb + (j0 / CELL_CLUSTER) * 2) + off,
                     min(32768u, box_bytes - off), &bar);
     }
+    if (SYM) {
+      for (int a = tid; a < jcount * 3; a += CELL_SWEEP_THREADS) jacc[a] = 0;
+      __syncthreads();
+    }
     mbar_wait(&bar, phase);
     phase ^= 1u;
 
-    for (int tile = warp_global; tile < ntile; tile += warp_stride) {
+    // symmetric mode: the i tiles are visited in `sym_passes` passes and the j accumulators are
+    // flushed after each, so that at most ntile * 32 / sym_passes i atoms feed one accumulator
+    const int tiles_per_pass = SYM ? (ntile + sym_passes - 1) / sym_passes : ntile;
+    for (int tile_first = 0; tile_first < ntile; tile_first += tiles_per_pass) {
+    const int tile_last = min(ntile, tile_first + tiles_per_pass);
+    for (int tile = tile_first + warp_global; tile < tile_last; tile += warp_stride) {
       T4 pi = ip[tile * CELL_TILE + lane];
       const int tagi = tag_decode(pi.w);
       // padding lanes go to the far side of the padding atoms (+1e18), so no pair of them ever
@@ -476,7 +507,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               }
             }
             const T4 pj = stg[k];
-            const int tagj = tag_decode(pj.w);
+            const int tagj = tag_decode(pj.w);  // (SYM: the accumulator slot)
             T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
             if (UNSAFE) pair_min_image<PBC>(dx, dy, dz, bx);
             const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -502,9 +533,16 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               for (int c = 0; c < NCH; ++c) en[c] += w * e[c];
               if (GRAD) {
                 coef *= w;
-                gx -= coef * dx;
-                gy -= coef * dy;
-                gz -= coef * dz;
+                const T fx = coef * dx, fy = coef * dy, fz = coef * dz;
+                gx -= fx;
+                gy -= fy;
+                gz -= fz;
+                if (SYM) {
+                  int* acc = jacc + tagj * 3;
+                  atomicAdd(acc, sym_fixed((float)fx, sym_scale));
+                  atomicAdd(acc + 1, sym_fixed((float)fy, sym_scale));
+                  atomicAdd(acc + 2, sym_fixed((float)fz, sym_scale));
+                }
               }
             }
           }
@@ -572,6 +610,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             pj.x -= ent.x;  // d = (x_j - shift) - x_i is the minimum image for a safe cluster
             pj.y -= ent.y;
             pj.z -= ent.z;
+            if (SYM)  // the accumulator slot of the atom within the chunk (-1: padding)
+              pj.w = tag_encode(
+                  tag_decode(pj.w) < 0 ? -1 : tag_decode(ent.w) * CELL_CLUSTER + (a & 7), T(0));
             stg[nbatch * CELL_CLUSTER + a] = pj;
           }
           batch_unsafe |= window_unsafe;
@@ -590,6 +631,30 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         g.w = T(0);
         ig[tile * CELL_TILE + lane] = g;
       }
+    }
+    if (SYM) {
+      // flush the j accumulators of this pass: the first pass writes, the others add (every j atom
+      // belongs to exactly one chunk, and the passes come in a fixed order)
+      __syncthreads();
+      T4* jg = jgrad + b * nj_pad + j0;
+      const T inv_scale = T(1) / T(sym_scale);
+      for (int a = tid; a < jcount; a += CELL_SWEEP_THREADS) {
+        T4 g;
+        g.x = T(jacc[3 * a]) * inv_scale;
+        g.y = T(jacc[3 * a + 1]) * inv_scale;
+        g.z = T(jacc[3 * a + 2]) * inv_scale;
+        g.w = T(0);
+        if (tile_first > 0) {
+          const T4 old = jg[a];
+          g.x += old.x;
+          g.y += old.y;
+          g.z += old.z;
+        }
+        jg[a] = g;
+        jacc[3 * a] = jacc[3 * a + 1] = jacc[3 * a + 2] = 0;
+      }
+      __syncthreads();
+    }
     }
   }
 

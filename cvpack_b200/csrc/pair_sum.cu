@@ -348,6 +348,7 @@ struct PairSumCV : cvp_cv {
   bool identical = false;  // group1 and group2 are the same set
   int use_cells = 1;       // option "cells": 1 = cell-sorted fast path when eligible, 0 = all pairs
   int nsplit_override = 0; // option "nsplit": CTAs per frame in the cell sweep (0 = automatic)
+  int use_sym = 1;         // option "sym": single symmetric sweep when eligible (pair_cells.cuh)
   DeviceBuffer d_g1, d_g2, d_tag1, d_tag2, d_ex_pairs, d_ex_atoms, d_ex_offsets, d_ex_partners;
   DeviceBuffer d_prm1[2], d_prm2[2], d_prm_atom[2];  // per dtype
 
@@ -417,6 +418,10 @@ struct PairSumCV : cvp_cv {
       std::swap(nsplit_override, value);
       return value;
     }
+    if (key == "sym") {
+      std::swap(use_sym, value);
+      return value;
+    }
     return cvp_cv::set_option(name, value);
   }
   size_t cell_sort_smem(int n) const {
@@ -452,6 +457,51 @@ struct PairSumCV : cvp_cv {
     pc.ke = (T)d.coulomb_constant;
     pc.neg_beta_over_rc = has_cutoff ? -d.beta / d.cutoff : -d.beta;
     return pc;
+  }
+
+  // Largest |dE/dr| of the pair function 1/(1+x^6) * switch on (0, cutoff), sampled in double.
+  double contacts6_max_slope() const {
+    const double r0 = d.r0, rc = d.cutoff, rs = d.switch_distance;
+    const bool sw_on = rs > 0 && rs < rc;
+    double worst = 0.0;
+    const int samples = 1 << 14;
+    for (int k = 1; k <= samples; ++k) {
+      const double r = rc * k / samples;
+      const double x = r / r0, x6 = pow(x, 6);
+      const double s = 1.0 / (1.0 + x6), ds = -6.0 * x6 / x * s * s / r0;
+      double sw = 1.0, dsw = 0.0;
+      if (sw_on && r > rs) {
+        const double t = (r - rs) / (rc - rs);
+        sw = 1.0 - t * t * t * (10.0 - 15.0 * t + 6.0 * t * t);
+        dsw = -30.0 * t * t * (1.0 - t) * (1.0 - t) / (rc - rs);
+      }
+      worst = std::max(worst, std::fabs(ds * sw + s * dsw));
+    }
+    return worst * 1.01;
+  }
+  // Decides whether run_cells may use the symmetric sweep; picks the number of passes over the i
+  // tiles and the fixed-point scale (a power of two) such that
+  //   scale * max|dE/dr| * (i atoms per pass) < 2^31   and   scale * max|dE/dr| < 2^22.
+  template <typename T, int KIND, bool OVERLAP>
+  bool sym_plan(bool need_grad, int nsplit, int ni_pad, float* scale, int* passes) const {
+    if (!std::is_same<T, float>::value || KIND != CVP_PAIR_CONTACTS || OVERLAP) return false;
+    if (!use_sym || !need_grad || nsplit != 1) return false;
+    if (d.step_kind != CVP_STEP_RATIONAL || (int)d.step_p0 != 6 || !(d.r0 > 0) || !(d.cutoff > 0))
+      return false;
+    const double slope = contacts6_max_slope();
+    if (!(slope > 0)) return false;
+    for (int p = 1; p <= 8; p *= 2) {
+      const double per_pass = (double)cell_round_up(cell_round_up(ni_pad, CELL_TILE) / CELL_TILE, p) /
+                              p * CELL_TILE;
+      const double limit = std::min(2147483648.0 / (slope * per_pass), 4194304.0 / slope);
+      const int exponent = (int)std::floor(std::log2(limit * 0.999));
+      if (exponent >= 18 || (p == 8 && exponent >= 16)) {
+        *scale = (float)std::ldexp(1.0, std::min(exponent, 24));
+        *passes = p;
+        return true;
+      }
+    }
+    return false;
   }
 
   // ---- cell-sorted fast path (pair_cells.cuh) ----
@@ -514,9 +564,11 @@ struct PairSumCV : cvp_cv {
           (int)(ex_pairs.size() / 2), box, a.box_mode, pc, excluded);
       CVP_LAUNCH_CHECK();
     }
-    const int jchunk = cell_jchunk<T>();
-    const size_t sweep_smem = cell_sweep_smem<T>();
-    (void)jchunk;
+    // symmetric mode (one sweep for both groups): FP32 contacts with 1/(1+x^6), disjoint groups, one
+    // CTA per frame, and a fixed-point scale of at least 2^16 that provably cannot overflow
+    float sym_scale = 0.f;
+    int sym_passes = 1;
+    const bool sym = sym_plan<T, KIND, OVERLAP>(need_grad, nsplit, n1p, &sym_scale, &sym_passes);
     auto sweep = [&](bool first, bool with_grad, const T* coef, double* energy) -> int {
       const T4* ip = first ? s1 : s2;
       const T4* jp = first ? s2 : s1;
@@ -532,12 +584,21 @@ struct PairSumCV : cvp_cv {
       if (fast6)
         kernel = with_grad ? cell_sweep_kernel<T, KIND, CPBC, OVERLAP, true, CAN_FAST6>
                            : cell_sweep_kernel<T, KIND, CPBC, OVERLAP, false, CAN_FAST6>;
+      size_t sweep_smem = cell_sweep_smem<T>(false);
+      T4* jout = nullptr;
+      if constexpr (std::is_same<T, float>::value && KIND == CVP_PAIR_CONTACTS && !OVERLAP) {
+        if (sym && first && with_grad) {
+          kernel = cell_sweep_kernel<T, KIND, CPBC, OVERLAP, true, true, true>;
+          sweep_smem = cell_sweep_smem<T>(true);
+          jout = gr2;
+        }
+      }
       CVP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sweep_smem));
       timer.begin("sweep", st);
       kernel<<<(unsigned)(B * nsplit), CELL_SWEEP_THREADS, sweep_smem, st>>>(
           ip, jp, jb, prm_atom, nip, njp, nsplit, box, a.box_mode, pc, coef, energy,
-          with_grad ? out : nullptr);
+          with_grad ? out : nullptr, jout, sym_scale, sym_passes);
       timer.end(st);
       CVP_LAUNCH_CHECK();
       return CVP_OK;
@@ -560,7 +621,7 @@ struct PairSumCV : cvp_cv {
       CVP_LAUNCH_CHECK();
     }
     if (!need_grad) return CVP_OK;
-    if ((status = sweep(false, true, frame_coef, nullptr)) != CVP_OK) return status;
+    if (!sym && (status = sweep(false, true, frame_coef, nullptr)) != CVP_OK) return status;
     if (!accumulate)
       CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
     const T gscale = KIND == CVP_PAIR_SOFTMIN ? T(1) : (T)d.scale;

@@ -232,3 +232,42 @@ def test_fused_streaming_kernel_vs_c_oracle(n, first, frames, sub, lag):
         # deterministic
         value3, grad3 = cv.getValueAndGradient(ctx)
         assert torch.equal(value3._value, value._value) and torch.equal(grad3, grad)
+
+
+@pytest.mark.parametrize("periodic", [True, False])
+def test_symmetric_sweep_vs_c_oracle(periodic):
+    """Single symmetric sweep (fixed-point j accumulators in shared memory, pair_cells.cuh): taken
+    for FP32 contacts between disjoint groups when one CTA handles a frame.  Compared with the C
+    oracle and with the two-sweep path; bitwise reproducible."""
+    rng = np.random.default_rng(36)
+    n, box = 9000, 4.48
+    x = lattice_frames(rng, 5, n, box)
+    system = unit_system(n)
+    cv = cvpack.NumberOfContacts(range(0, 5000), range(5000, n), plain_nonbonded(n, periodic),
+                                 thresholdDistance=0.6)
+    cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, [box] * 3 if periodic else None)
+    native = ctx._native_cv(cv)  # pylint: disable=protected-access
+    native.set_option("nsplit", 1)
+    native.set_option("time_kernels", 1)
+    value, grad = cv.getValueAndGradient(ctx)
+    assert native.kernel_time("sweep")[1] == 1, "expected one (symmetric) sweep"
+    stored = ctx.getPositions().double().cpu().numpy()
+    ref_value, ref_grad = c_oracle.contacts_batch(
+        stored, range(0, 5000), range(5000, n), (), np.diag([box] * 3) if periodic else None,
+        r0=0.6, rc=1.2, rs=0.9,
+    )
+    v = value._value.double().cpu().numpy()
+    g = grad.double().cpu().numpy()
+    assert np.abs(v - ref_value).max() <= 1e-5 * np.abs(ref_value).max()
+    assert np.abs(g - ref_grad).max() <= 1e-5 * np.abs(ref_grad).max()
+    # a pair sum exerts no net force
+    assert np.abs(g.sum(axis=1)).max() <= 1e-3 * np.abs(g).max()
+    value_again, grad_again = cv.getValueAndGradient(ctx)
+    assert torch.equal(value_again._value, value._value) and torch.equal(grad_again, grad)
+    native.kernel_time("sweep")
+    native.set_option("sym", 0)
+    value2, grad2 = cv.getValueAndGradient(ctx)
+    assert native.kernel_time("sweep")[1] == 2
+    assert torch.allclose(value2._value, value._value, rtol=1e-6)
+    assert (grad2 - grad).abs().max() <= 5e-6 * grad.abs().max()
