@@ -201,6 +201,23 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "source": "fallback"}
 
 
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the
+# committed `ncu --set full` captures, per frame, so that it can be quoted per launch of this run.
+NCU_TRAFFIC = {
+    "contacts": dict(bytes=2.145803e9 + 1.389061e9, frames=1483, source="profiles/r1_ncu_cell_sweep_sym.txt"),
+    "rmsd": dict(bytes=4.914634e9 + 2.450167e9, frames=2048, source="profiles/r1_ncu_rmsd_fused_final.txt"),
+    "rg": dict(bytes=3.355705e9 + 2.418428e9, frames=2048, source="profiles/r1_ncu_rg_fused.txt"),
+}
+
+
+def ncu_traffic(workload: str, frames_per_launch: float):
+    """(bytes per launch, provenance) from the committed ncu capture, scaled by frames per launch."""
+    entry = NCU_TRAFFIC.get(workload)
+    if entry is None or not frames_per_launch:
+        return None, None
+    return entry["bytes"] / entry["frames"] * frames_per_launch, entry["source"]
+
+
 # ---- CPU oracle arm ------------------------------------------------------------------------------------
 def cpu_oracle_run(workload: str, spec: dict, positions: np.ndarray, reference) -> float:
     """Seconds the C oracle (OpenMP over frames, all host threads) needs for `positions`."""
@@ -376,10 +393,12 @@ def run_ours(args, spec: dict) -> None:
         flop_per_pair = 21.0 + 39.0 * p_in
         flop_per_step = frames * (n // 2) * (n // 2) * flop_per_pair
         achieved = args.steps * flop_per_step / (ms * 1e-3) / 1e12 if count else None
+        traffic, traffic_source = ncu_traffic("contacts", frames * args.steps / count if count else 0)
         roofline = {
             "bound": "fp32", "kernel": "cell_sweep_kernel (or pair_sweep_kernel when cells=0)",
             "achieved": achieved, "peak": fp32_peak,
-            "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None,
+            "traffic": traffic, "traffic_source": traffic_source,
             "peak_source": "FFMA microbenchmark in this run (cvp_measure_fp32_peak)",
             "launches": count, "avg_launch_ms": ms / count if count else None,
             "kernel_share_of_step": ms / elapsed_ms,
@@ -394,10 +413,14 @@ def run_ours(args, spec: dict) -> None:
         # algorithmic bytes: 12 B/atom read once + 12 B/atom gradient written = 24 B/atom/frame
         bytes_per_step = frames * n * 24.0
         achieved = args.steps * bytes_per_step / (total_ms * 1e-3) / 1e9
+        fused = any(name.endswith("_fused") for name in used)
+        traffic, traffic_source = ncu_traffic(
+            args.workload, frames * args.steps / total_launches if fused and total_launches else 0)
         roofline = {
             "bound": "hbm", "kernel": "+".join(sorted(used)), "achieved": achieved,
             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
+            "traffic": traffic, "traffic_source": traffic_source,
+            "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
             "launches": total_launches, "avg_launch_ms": total_ms / max(total_launches, 1),
             "kernel_share_of_step": total_ms / elapsed_ms,
             "algorithmic_bytes_per_frame": n * 24,

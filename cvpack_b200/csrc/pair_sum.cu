@@ -531,6 +531,12 @@ struct PairSumCV : cvp_cv {
       nsplit = (int)std::max<int64_t>(1, div_up(want, B));
       const int ntile = std::min(n1p, n2p) / CELL_TILE;
       nsplit = std::max(1, std::min(nsplit, ntile / (CELL_SWEEP_THREADS / 32)));
+      // the symmetric sweep (half the pair work) needs one CTA per frame: worth a ragged last wave
+      // as soon as there is about one CTA per SM
+      float unused_scale;
+      int unused_passes;
+      if (B >= 148 && sym_plan<T, KIND, OVERLAP>(need_grad, 1, n1p, &unused_scale, &unused_passes))
+        nsplit = 1;
     }
 
     Carver carve(ws);
