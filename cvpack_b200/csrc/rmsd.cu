@@ -23,6 +23,7 @@
 //   gradient  one thread per (frame, active atom): sum over the atom's entries (CSR), single writer
 #include "common.cuh"
 #include "stream_fused.cuh"
+#include "rmsd_multi.cuh"
 
 namespace cvp {
 namespace {
@@ -403,7 +404,10 @@ __global__ void rmsd_solve_kernel(const double* __restrict__ partials, int nslic
                                   const int32_t* __restrict__ group_size,
                                   const double* __restrict__ group_gy, int num_groups,
                                   int64_t num_frames, RmsdSolution* __restrict__ solution,
-                                  double* __restrict__ seg_centroid, int nseg) {
+                                  double* __restrict__ seg_centroid, int nseg,
+                                  int shared_moments = 0) {
+  // shared_moments = SK > 0: every group covers the same atoms (rmsd_multi.cuh); segment s owns the
+  // slices [s * SK, (s + 1) * SK) and sum x, sum |x|^2 are stored once, in the slices of group 0
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= num_frames * num_groups) return;
   const int64_t b = t / num_groups;
@@ -412,12 +416,15 @@ __global__ void rmsd_solve_kernel(const double* __restrict__ partials, int nslic
   double gx = 0.0;
   for (int seg = group_seg_offsets[g]; seg < group_seg_offsets[g + 1]; ++seg) {
     double sx = 0, sy = 0, sz = 0, s2 = 0;
-    for (int s = seg_slice_offsets[seg]; s < seg_slice_offsets[seg + 1]; ++s) {
+    const int s_begin = shared_moments ? seg * shared_moments : seg_slice_offsets[seg];
+    const int s_end = shared_moments ? (seg + 1) * shared_moments : seg_slice_offsets[seg + 1];
+    for (int s = s_begin; s < s_end; ++s) {
       const double* p = partials + ((size_t)b * nslice + s) * 13;
-      sx += p[0];
-      sy += p[1];
-      sz += p[2];
-      s2 += p[3];
+      const double* pm = shared_moments ? partials + ((size_t)b * nslice + (s - s_begin)) * 13 : p;
+      sx += pm[0];
+      sy += pm[1];
+      sz += pm[2];
+      s2 += pm[3];
 #pragma unroll
       for (int k = 0; k < 9; ++k) r[k] += p[4 + k];
     }
@@ -615,6 +622,10 @@ struct RmsdCV : cvp_cv {
   int fused_slots = 0;  // option "fused_slots": auxiliary-data slots per CTA (0 = planner)
   int fused_hints = 3;  // option "fused_hints": L2 eviction hints (see FusedGeom::l2_hints)
   int fast_first = 0, fast_nslice = 0;
+  // many references over one contiguous atom set (rmsd_multi.cuh)
+  bool multi = false;
+  int use_multi = 1;  // option "multi"
+  int multi_first = 0, multi_n = 0, multi_sk_max = 1;
   std::vector<float> ref_f32;
   std::vector<int32_t> fast_seg_slice_offsets;
   std::vector<double> fast_gy;
@@ -679,6 +690,10 @@ struct RmsdCV : cvp_cv {
       std::swap(use_fused, value);
       return value;
     }
+    if (key == "multi") {
+      std::swap(use_multi, value);
+      return value;
+    }
     if (key == "fused_lag") {
       std::swap(fused_lag, value);
       return value;
@@ -734,6 +749,44 @@ struct RmsdCV : cvp_cv {
           accumulate, st);
       timer.end(st);
       return status;
+    }
+    const bool use_multi_path = multi && use_multi && std::is_same<T, float>::value;
+    if (use_multi_path) {
+      // slices over the atoms: about two waves of CTAs (2 per SM)
+      const int64_t tiles = div_up(B, MULTI_TF) * div_up(num_groups, MULTI_TG);
+      const int multi_sk =
+          (int)std::max<int64_t>(1, std::min<int64_t>(multi_sk_max, (4 * sm_count() + tiles / 2) / tiles));
+      const int ns_multi = num_groups * multi_sk;
+      const dim3 cov_grid((unsigned)div_up(B, MULTI_TF), (unsigned)div_up(num_groups, MULTI_TG),
+                          (unsigned)multi_sk);
+      timer.begin("rmsd_multi_cov", st);
+      rmsd_multi_cov_kernel<<<cov_grid, MULTI_THREADS, 0, st>>>(
+          reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+          static_cast<const double*>(d_ref.ptr), num_groups, B, multi_sk, partials);
+      timer.end(st);
+      CVP_LAUNCH_CHECK();
+      rmsd_solve_kernel<<<(unsigned)div_up(B * num_groups, 64), 64, 0, st>>>(
+          partials, ns_multi, static_cast<const int32_t*>(d_group_seg_offsets.ptr),
+          nullptr, static_cast<const int32_t*>(d_seg_size.ptr),
+          static_cast<const int32_t*>(d_group_size.ptr), static_cast<const double*>(d_group_gy.ptr),
+          num_groups, B, solution, seg_centroid, nseg, multi_sk);
+      CVP_LAUNCH_CHECK();
+      rmsd_combine_kernel<T><<<(unsigned)div_up(B, 128), 128, 0, st>>>(
+          solution, static_cast<const int32_t*>(d_group_size.ptr), num_groups, cp, value,
+          group_factor, accumulate ? 1 : 0, B);
+      CVP_LAUNCH_CHECK();
+      if (grad == nullptr) return CVP_OK;
+      if (!accumulate && !dense)
+        CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+      const dim3 grad_grid((unsigned)div_up(B, MULTI_TF), (unsigned)div_up(multi_n, MULTI_TA));
+      timer.begin("rmsd_multi_gradient", st);
+      rmsd_multi_gradient_kernel<RmsdSolution><<<grad_grid, MULTI_THREADS, 0, st>>>(
+          reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+          static_cast<const double*>(d_ref.ptr), num_groups, B, solution, group_factor,
+          seg_centroid, nseg, reinterpret_cast<float*>(grad), accumulate ? 1 : 0);
+      timer.end(st);
+      CVP_LAUNCH_CHECK();
+      return CVP_OK;
     }
     const int ns = use_fast ? fast_nslice : nslice;
     if (use_fast) {
@@ -929,6 +982,23 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
       cv->fast_gy.assign(1, gy);
       cv->ref_perm = fused_permute_doubles(cv->ref_f32.data(), (size_t)E);
       cv->fast_seg_slice_offsets = {0, cv->fast_nslice};
+    }
+  }
+  // many references, one atom set: G >= 2 single-segment groups that all list atoms first,
+  // first + 1, ..., first + n - 1 in this order
+  if (G >= 2 && cv->nseg == G && E % G == 0) {
+    const int64_t n = E / G;
+    bool same = n >= 64;
+    for (int g = 0; g < G && same; ++g) same = desc->group_offsets[g] == g * n;
+    for (int64_t e = 0; e < E && same; ++e)
+      same = cv->entry_atom[e] == cv->entry_atom[0] + (int32_t)(e % n);
+    if (same) {
+      cv->multi = true;
+      cv->multi_first = cv->entry_atom[0];
+      cv->multi_n = (int)n;
+      // slices over the atoms: at least 512 atoms each, never more than the generic path reserves
+      // workspace for (ceil(n / 1024) per group)
+      cv->multi_sk_max = (int)std::max<int64_t>(1, std::min<int64_t>({16, n / 512, div_up(n, 1024)}));
     }
   }
   *out = cv;

@@ -271,3 +271,38 @@ def test_symmetric_sweep_vs_c_oracle(periodic):
     assert native.kernel_time("sweep")[1] == 2
     assert torch.allclose(value2._value, value._value, rtol=1e-6)
     assert (grad2 - grad).abs().max() <= 5e-6 * grad.abs().max()
+
+
+@pytest.mark.parametrize("metric", ["progress", "deviation"])
+@pytest.mark.parametrize("n_group,first,frames,milestones", [(300, 8, 70, 5), (1000, 0, 33, 37)])
+def test_path_many_references_one_atom_set(metric, n_group, first, frames, milestones):
+    """PathInRMSDSpace whose milestones all list the same contiguous atoms takes the tiled
+    double-precision contractions of rmsd_multi.cuh: against the NumPy oracle and against the
+    generic per-entry kernels."""
+    rng = np.random.default_rng(37)
+    n = first + n_group + 5
+    system = helpers.make_system(n, rng)
+    start, end = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+    atoms = list(range(first, first + n_group))
+    refs = []
+    for k in range(milestones):
+        conf = start + (end - start) * k / (milestones - 1) + 0.01 * rng.normal(size=(n, 3))
+        refs.append({a: conf[a] for a in atoms})
+    lam = rng.uniform(0.1, 0.9, size=frames)[:, None, None]
+    x = start[None] + (end - start)[None] * lam + 0.02 * rng.normal(size=(frames, n, 3))
+    cv = cvpack.PathInRMSDSpace(getattr(cvpack.path, metric), refs, n, 0.3)
+    cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x)
+    native = ctx._native_cv(cv)  # pylint: disable=protected-access
+    native.set_option("time_kernels", 1)
+    helpers.check_against_oracle(cv, system, x, None, "single", 5e-5, 5e-5, context=ctx)
+    assert native.kernel_time("rmsd_multi_cov")[1] >= 1, "the multi-reference kernels did not run"
+    value, grad = cv.getValueAndGradient(ctx)
+    native.set_option("multi", 0)
+    value2, grad2 = cv.getValueAndGradient(ctx)
+    native.set_option("multi", 1)
+    assert torch.allclose(value2._value, value._value, rtol=2e-6, atol=1e-7)
+    assert (grad2 - grad).abs().max() <= 2e-6 * grad.abs().max()
+    outside = torch.ones(n, dtype=torch.bool)
+    outside[atoms] = False
+    assert not grad[:, outside].any()
