@@ -763,6 +763,10 @@ struct RmsdCV : cvp_cv {
       rmsd_multi_cov_kernel<<<cov_grid, MULTI_THREADS, 0, st>>>(
           reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
           static_cast<const double*>(d_ref.ptr), num_groups, B, multi_sk, partials);
+      CVP_LAUNCH_CHECK();
+      rmsd_multi_moments_kernel<<<(unsigned)div_up(B * multi_sk * 32, 256), 256, 0, st>>>(
+          reinterpret_cast<const float*>(pos), N, multi_first, multi_n, num_groups, B, multi_sk,
+          partials);
       timer.end(st);
       CVP_LAUNCH_CHECK();
       rmsd_solve_kernel<<<(unsigned)div_up(B * num_groups, 64), 64, 0, st>>>(
@@ -779,8 +783,15 @@ struct RmsdCV : cvp_cv {
       if (!accumulate && !dense)
         CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
       const dim3 grad_grid((unsigned)div_up(B, MULTI_TF), (unsigned)div_up(multi_n, MULTI_TA));
+      static bool multi_configured = false;
+      if (!multi_configured) {
+        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_gradient_kernel<RmsdSolution>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)MULTI_GRAD_SMEM));
+        multi_configured = true;
+      }
       timer.begin("rmsd_multi_gradient", st);
-      rmsd_multi_gradient_kernel<RmsdSolution><<<grad_grid, MULTI_THREADS, 0, st>>>(
+      rmsd_multi_gradient_kernel<RmsdSolution><<<grad_grid, MULTI_THREADS, MULTI_GRAD_SMEM, st>>>(
           reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
           static_cast<const double*>(d_ref.ptr), num_groups, B, solution, group_factor,
           seg_centroid, nseg, reinterpret_cast<float*>(grad), accumulate ? 1 : 0);

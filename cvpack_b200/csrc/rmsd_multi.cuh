@@ -16,7 +16,7 @@
 //               and are produced once (group 0's slices).
 //   gradient    g[f][a] = F_f (x[f][a] - c_f) - sum_g W[f][g] y^[g][a],   W = factor[f][g] U^T[f][g]
 //               [3B x 3G] . [3G x n]: CTA tile 32 frames x 64 atoms, thread tile 2 frames x 4 atoms
-//               (72 DFMA per group and thread), groups in chunks of 8.
+//               (72 DFMA per group and thread), groups in chunks of 16.
 // Double precision throughout, like the generic kernels: (x - c) - U^T y^ cancels three digits
 // and the path weights cancel again across milestones.  Deterministic (fixed summation order).
 #pragma once
@@ -31,7 +31,7 @@ constexpr int MULTI_TF = 32;      // frames per CTA tile
 constexpr int MULTI_TG = 32;      // groups per CTA tile (covariance)
 constexpr int MULTI_KA = 8;       // atoms per stage (covariance)
 constexpr int MULTI_TA = 64;      // atoms per CTA tile (gradient)
-constexpr int MULTI_KG = 8;       // groups per stage (gradient)
+constexpr int MULTI_KG = 16;      // groups per stage (gradient)
 
 // ---- covariance ----------------------------------------------------------------------------------
 // grid = (frame tiles, group tiles, SK); partials[(b * ns + g * SK + sk) * 13 + ...]
@@ -60,8 +60,6 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int k = 0; k < 9; ++k) acc[i][j][k] = 0.0;
-  double mom[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-  const bool do_moments = blockIdx.y == 0 && tx == 0;
 
   // loader roles: 32 rows x ROW values per tile and stage, NQ per thread.  X: (frame, atom, comp)
   // with the ROW floats of a frame's MULTI_KA atoms contiguous in global memory; Y: (group, atom,
@@ -123,15 +121,6 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
           for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int d = 0; d < 3; ++d) acc[i][j][3 * c + d] = fma(xv[i][c], yv[j][d], acc[i][j][3 * c + d]);
-      if (do_moments) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          mom[i][0] += xv[i][0];
-          mom[i][1] += xv[i][1];
-          mom[i][2] += xv[i][2];
-          mom[i][3] = fma(xv[i][0], xv[i][0], fma(xv[i][1], xv[i][1], fma(xv[i][2], xv[i][2], mom[i][3])));
-        }
-      }
     }
     if (more) store_regs(buf ^ 1);
     __syncthreads();
@@ -148,13 +137,41 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
       double* out = partials + ((size_t)f * ns + (size_t)g * SK + sk) * 13;
 #pragma unroll
       for (int k = 0; k < 9; ++k) out[4 + k] = acc[i][j][k];
-      if (g != 0) out[0] = out[1] = out[2] = out[3] = 0.0;  // (the solve reads group 0's moments)
+      // (out[0..3] of group 0 come from rmsd_multi_moments_kernel; the other groups' are unused)
     }
-    if (do_moments) {
-      double* out = partials + ((size_t)f * ns + sk) * 13;  // group 0, slice sk
+  }
+}
+
+// sum x, sum |x|^2 of a frame over the same atom slices; one warp per (frame, slice), written to
+// group 0's slice records
+__global__ void rmsd_multi_moments_kernel(const float* __restrict__ pos, int64_t num_atoms,
+                                          int first_atom, int n, int num_groups,
+                                          int64_t num_frames, int SK,
+                                          double* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (w >= num_frames * SK) return;
+  const int64_t f = w / SK;
+  const int sk = (int)(w - f * SK);
+  const int chunks_total = (n + MULTI_KA - 1) / MULTI_KA;
+  const int chunks_per = (chunks_total + SK - 1) / SK;
+  const int a_begin = min(n, sk * chunks_per * MULTI_KA);
+  const int a_end = min(n, (sk + 1) * chunks_per * MULTI_KA);
+  const float* p = pos + (f * num_atoms + first_atom) * 3;
+  double v[4] = {0, 0, 0, 0};
+  for (int a = a_begin + lane; a < a_end; a += 32) {
+    const double x = p[3 * (int64_t)a], y = p[3 * (int64_t)a + 1], z = p[3 * (int64_t)a + 2];
+    v[0] += x;
+    v[1] += y;
+    v[2] += z;
+    v[3] = fma(x, x, fma(y, y, fma(z, z, v[3])));
+  }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) out[k] = mom[i][k];
-    }
+  for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+    double* out = partials + ((size_t)f * num_groups * SK + sk) * 13;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = v[k];
   }
 }
 
@@ -168,8 +185,10 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
                                const double* __restrict__ factor,
                                const double* __restrict__ centroid /* [frame][nseg][3], seg 0 */,
                                int nseg, float* __restrict__ grad, int accumulate) {
-  __shared__ __align__(16) double Ws[MULTI_KG][MULTI_TF][10];  // f * U^T (9), f
-  __shared__ __align__(16) double Ys[MULTI_KG][MULTI_TA][3];
+  extern __shared__ __align__(16) double multi_smem[];
+  double (*Ws)[MULTI_TF][10] = reinterpret_cast<double (*)[MULTI_TF][10]>(multi_smem);  // f U^T, f
+  double (*Ys)[MULTI_TA][3] =
+      reinterpret_cast<double (*)[MULTI_TA][3]>(multi_smem + MULTI_KG * MULTI_TF * 10);
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;  // frames 2ty, 2ty+1; atoms 4tx .. 4tx+3 of the tile
   const int64_t f0 = (int64_t)blockIdx.x * MULTI_TF;
@@ -186,9 +205,10 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
 
   for (int g0 = 0; g0 < num_groups; g0 += MULTI_KG) {
     __syncthreads();
-    // W tile: MULTI_KG groups x 32 frames, one (group, frame) pair per thread and pass
+    // W tile: MULTI_KG groups x 32 frames, one (frame, group) pair per thread and pass; consecutive
+    // threads take consecutive groups of a frame (contiguous 80-byte solution records)
     for (int idx = tid; idx < MULTI_KG * MULTI_TF; idx += MULTI_THREADS) {
-      const int gl = idx / MULTI_TF, fl = idx - gl * MULTI_TF;
+      const int fl = idx / MULTI_KG, gl = idx - fl * MULTI_KG;
       const int g = g0 + gl;
       const int64_t f = f0 + fl;
       double w[10];
@@ -271,6 +291,9 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
     }
   }
 }
+
+constexpr size_t MULTI_GRAD_SMEM =
+    sizeof(double) * (MULTI_KG * MULTI_TF * 10 + MULTI_KG * MULTI_TA * 3);
 
 }  // namespace
 }  // namespace cvp
