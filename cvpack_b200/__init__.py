@@ -29,6 +29,7 @@ from .rmsd import RMSD  # noqa: F401
 from .sheet_rmsd_content import SheetRMSDContent  # noqa: F401
 from .shortest_distance import ShortestDistance  # noqa: F401
 from .torsion import Torsion  # noqa: F401
+from .torsion_similarity import TorsionSimilarity  # noqa: F401
 
 __all__ = [
     "Angle",
@@ -52,6 +53,7 @@ __all__ = [
     "ShortestDistance",
     "System",
     "Torsion",
+    "TorsionSimilarity",
     "Vec3",
     "shard_frames",
 ]

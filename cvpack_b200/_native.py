@@ -23,7 +23,7 @@ CVP_STEP_RATIONAL, CVP_STEP_HEAVISIDE, CVP_STEP_RATIONAL_PAIR, CVP_STEP_PLUMED =
 CVP_PAIR_CONTACTS, CVP_PAIR_ATTRACTION, CVP_PAIR_SOFTMIN = 0, 1, 2
 CVP_COMBINE_IDENTITY, CVP_COMBINE_STEP_SUM = 0, 1
 CVP_COMBINE_PATH_PROGRESS, CVP_COMBINE_PATH_DEVIATION = 2, 3
-CVP_TERM_IDENTITY, CVP_TERM_BOXCAR = 0, 1
+CVP_TERM_IDENTITY, CVP_TERM_BOXCAR, CVP_TERM_HALF_COSINE = 0, 1, 2
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)

@@ -1,9 +1,10 @@
-// Sums of bonded terms (distances, angles, dihedrals), value + gradient, for a batch of frames:
-// Distance, Angle, Torsion and Helix{Torsion,Angle,HBond}Content.
+// Sums of bonded terms (distances, angles, dihedrals, pairs of dihedrals), value + gradient, for a
+// batch of frames: Distance, Angle, Torsion, Helix{Torsion,Angle,HBond}Content, TorsionSimilarity.
 //
 // Replaces CustomBondForce / CustomAngleForce / CustomTorsionForce with one expression for all
 // terms (cvpack/distance.py:57-59, angle.py:73-75, torsion.py:80-82,
-// helix_torsion_content.py:126-145, helix_angle_content.py:118-128, helix_hbond_content.py:104-114).
+// helix_torsion_content.py:126-145, helix_angle_content.py:118-128, helix_hbond_content.py:104-114)
+// and the 8-particle CustomCompoundBondForce of torsion_similarity.py:89-93.
 //
 // Stages (one stream, deterministic):
 //   terms     one thread per (frame, term): q, f(q) and the gradient on the term's 2-4 atoms
@@ -36,6 +37,37 @@ __device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3
   c[0] = a[1] * b[2] - a[2] * b[1];
   c[1] = a[2] * b[0] - a[0] * b[2];
   c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// dihedral of four atoms and its gradient; sign convention of cvpack/torsion.py:22-33
+template <int PBC>
+__device__ __forceinline__ double torsion_geometry(const double (&r0)[3], const double (&r1)[3],
+                                                   const double (&r2)[3], const double (&r3)[3],
+                                                   const Box<double>& box, double (&g0)[3],
+                                                   double (&g1)[3], double (&g2)[3],
+                                                   double (&g3)[3]) {
+  double f[3], gv[3], h[3], fxh[3], a[3], b[3];
+  delta<PBC>(r0, r1, box, f);
+  delta<PBC>(r2, r1, box, gv);
+  delta<PBC>(r3, r2, box, h);
+  const double gg = dot3(gv, gv);
+  const double ng = sqrt(gg);
+  cross3(f, h, fxh);
+  const double fu = dot3(f, gv) / ng, hu = dot3(h, gv) / ng;
+  const double q = atan2(dot3(fxh, gv) / ng, dot3(f, h) - fu * hu);
+  cross3(f, gv, a);
+  cross3(h, gv, b);
+  const double ca = ng / dot3(a, a), cb = -ng / dot3(b, b);
+  const double pf = dot3(f, gv) / gg, ph = dot3(h, gv) / gg;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double d1 = ca * a[c], d4 = cb * b[c];
+    g0[c] = d1;
+    g3[c] = d4;
+    g1[c] = -d1 + pf * d1 + ph * d4;
+    g2[c] = -d4 - pf * d1 - ph * d4;
+  }
+  return q;
 }
 
 // q and dq/dr for the A atoms of one term; coordinates promoted to double (a handful of terms per
@@ -71,30 +103,17 @@ __device__ __forceinline__ double term_geometry(const double (&r)[A][3], const B
       g[1][c] = -(g1 + g3);
     }
     return acos(cosine);
+  } else if (A == 4) {
+    return torsion_geometry<PBC>(r[0], r[1], r[2], r[3], box, g[0], g[1], g[2], g[3]);
   } else {
-    // sign convention of cvpack/torsion.py:22-33
-    double f[3], gv[3], h[3], fxh[3], a[3], b[3];
-    delta<PBC>(r[0], r[1], box, f);
-    delta<PBC>(r[2], r[1], box, gv);
-    delta<PBC>(r[3], r[2], box, h);
-    const double g2 = dot3(gv, gv);
-    const double ng = sqrt(g2);
-    cross3(f, h, fxh);
-    const double fu = dot3(f, gv) / ng, hu = dot3(h, gv) / ng;
-    const double q = atan2(dot3(fxh, gv) / ng, dot3(f, h) - fu * hu);
-    cross3(f, gv, a);
-    cross3(h, gv, b);
-    const double ca = ng / dot3(a, a), cb = -ng / dot3(b, b);
-    const double pf = dot3(f, gv) / g2, ph = dot3(h, gv) / g2;
+    // A == 8: q = dihedral(p1..p4) - dihedral(p5..p8)  (torsion_similarity.py:90)
+    const double q1 = torsion_geometry<PBC>(r[0], r[1], r[2], r[3], box, g[0], g[1], g[2], g[3]);
+    const double q2 = torsion_geometry<PBC>(r[4], r[5], r[6], r[7], box, g[4], g[5], g[6], g[7]);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const double d1 = ca * a[c], d4 = cb * b[c];
-      g[0][c] = d1;
-      g[3][c] = d4;
-      g[1][c] = -d1 + pf * d1 + ph * d4;
-      g[2][c] = -d4 - pf * d1 - ph * d4;
-    }
-    return q;
+    for (int a = 4; a < 8; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[a][c] = -g[a][c];
+    return q1 - q2;
   }
 }
 
@@ -128,6 +147,11 @@ __global__ void bonded_terms_kernel(const T* __restrict__ pos, int64_t num_atoms
   if (tp.function == CVP_TERM_IDENTITY) {
     f = tp.coefficient * q;
     df = tp.coefficient;
+  } else if (tp.function == CVP_TERM_HALF_COSINE) {
+    // 0.5 (1 + cos(min(q, 2 pi - q))): cos is even and periodic, and both branches of the min have
+    // the derivative -sin q, so the expression of torsion_similarity.py:89 is 0.5 (1 + cos q)
+    f = tp.coefficient * 0.5 * (1.0 + cos(q));
+    df = -tp.coefficient * 0.5 * sin(q);
   } else {
     const double x = (q - reference[k]) * tp.inv_tolerance;
     const double xp1 = powi(x, tp.exponent - 1);
@@ -255,6 +279,7 @@ struct BondedCV : cvp_cv {
   int run_type(const EvalArgs& a, void* ws) {
     if (atoms_per_term == 2) return run_atoms<T, 2>(a, ws);
     if (atoms_per_term == 3) return run_atoms<T, 3>(a, ws);
+    if (atoms_per_term == 8) return run_atoms<T, 8>(a, ws);
     return run_atoms<T, 4>(a, ws);
   }
   int run(const EvalArgs& a, void* ws) override {
@@ -267,10 +292,12 @@ struct BondedCV : cvp_cv {
 int bonded_create(const cvp_bonded_desc* desc, cvp_cv** out) {
   CVP_REQUIRE(desc != nullptr && out != nullptr, "null argument");
   CVP_REQUIRE(desc->num_atoms > 0 && desc->num_terms > 0 && desc->atoms, "no bonded terms");
-  CVP_REQUIRE(desc->atoms_per_term >= 2 && desc->atoms_per_term <= 4,
-              "bonded terms have 2, 3 or 4 atoms");
-  CVP_REQUIRE(desc->function == CVP_TERM_IDENTITY || desc->function == CVP_TERM_BOXCAR,
+  CVP_REQUIRE((desc->atoms_per_term >= 2 && desc->atoms_per_term <= 4) || desc->atoms_per_term == 8,
+              "bonded terms have 2, 3, 4 or (pairs of dihedrals) 8 atoms");
+  CVP_REQUIRE(desc->function >= CVP_TERM_IDENTITY && desc->function <= CVP_TERM_HALF_COSINE,
               "unknown term function");
+  CVP_REQUIRE((desc->atoms_per_term == 8) == (desc->function == CVP_TERM_HALF_COSINE),
+              "the half-cosine function belongs to 8-atom terms (pairs of dihedrals)");
   if (desc->function == CVP_TERM_BOXCAR)
     CVP_REQUIRE(desc->reference && desc->tolerance > 0 && desc->half_exponent >= 1,
                 "boxcar terms need references, a positive tolerance and an exponent >= 1");

@@ -156,21 +156,24 @@ typedef struct {
 
 int cvp_gyration_create(const cvp_gyration_desc* desc, cvp_cv** out);
 
-/* ---- bonded terms: Distance, Angle, Torsion, Helix{Torsion,Angle,HBond}Content ---------------- */
+/* ---- bonded terms: Distance, Angle, Torsion, Helix{Torsion,Angle,HBond}Content,
+ *      TorsionSimilarity --------------------------------------------------------------------------- */
 /* Replaces CustomBondForce / CustomAngleForce / CustomTorsionForce with one expression for all
  * terms (distance.py:57-59, angle.py:73-75, torsion.py:80-82, helix_torsion_content.py:126-145,
  * helix_angle_content.py:118-128, helix_hbond_content.py:104-114).
- * value = sum_t f(q_t): q = |r2-r1| (2 atoms), acos angle at atom 2 (3 atoms), or the dihedral
- * (4 atoms, sign convention of torsion.py:22-33).                                                 */
+ * value = sum_t f(q_t): q = |r2-r1| (2 atoms), acos angle at atom 2 (3 atoms), the dihedral
+ * (4 atoms, sign convention of torsion.py:22-33), or the difference of two dihedrals (8 atoms:
+ * the CustomCompoundBondForce of torsion_similarity.py:89-93).                                     */
 enum {
   CVP_TERM_IDENTITY = 0,          /* f(q) = coefficient * q                                        */
-  CVP_TERM_BOXCAR = 1             /* f(q) = coefficient / (1 + x^(2m)), x = (q - ref_t)/tolerance   */
+  CVP_TERM_BOXCAR = 1,            /* f(q) = coefficient / (1 + x^(2m)), x = (q - ref_t)/tolerance   */
+  CVP_TERM_HALF_COSINE = 2        /* f(q) = coefficient * (1 + cos q)/2; 8-atom terms only          */
 };
 
 typedef struct {
   int32_t num_atoms;
   int32_t num_terms;
-  int32_t atoms_per_term;         /* 2, 3 or 4                                                     */
+  int32_t atoms_per_term;         /* 2, 3, 4 or 8                                                  */
   const int32_t* atoms;           /* [num_terms][atoms_per_term]                                   */
   int32_t function;
   const double* reference;        /* [num_terms] (CVP_TERM_BOXCAR), may be NULL otherwise          */

@@ -148,6 +148,29 @@ def torsion(x: np.ndarray, a1: int, a2: int, a3: int, a4: int, box: t.Optional[n
     return theta, g
 
 
+def torsion_similarity(
+    x: np.ndarray,
+    first: t.Sequence[t.Sequence[int]],
+    second: t.Sequence[t.Sequence[int]],
+    box: t.Optional[np.ndarray] = None,
+):
+    """
+    sum_i 0.5*(1 + cos(min(delta_i, 2*pi - delta_i))), delta_i = dihedral(first_i) -
+    dihedral(second_i)  (torsion_similarity.py:89-93).  Lepton differentiates min(a, b) by the
+    branch taken: d/d delta is -sin(delta) on the first branch and +sin(2*pi - delta) = -sin(delta)
+    on the second, so the gradient is -0.5 sin(delta_i) (grad phi1_i - grad phi2_i) either way.
+    """
+    total = 0.0
+    grad = np.zeros_like(x)
+    for one, two in zip(first, second):
+        q1, g1 = torsion(x, *one, box=box)
+        q2, g2 = torsion(x, *two, box=box)
+        delta = q1 - q2
+        total += 0.5 * (1.0 + np.cos(min(delta, 2 * np.pi - delta)))
+        grad += -0.5 * np.sin(delta) * (g1 - g2)
+    return total, grad
+
+
 def bonded_sum(
     x: np.ndarray,
     terms: t.Sequence[t.Sequence[int]],

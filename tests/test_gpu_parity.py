@@ -47,6 +47,21 @@ def test_bonded(precision, boxname):
     run(cvpack.Torsion(3, 17, 5, 9, pbc=pbc), system, x, box, precision)
 
 
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("boxname", ["none", "ortho", "triclinic"])
+def test_torsion_similarity(precision, boxname):
+    rng = np.random.default_rng(12)
+    box = BOXES[boxname]
+    system = helpers.make_system(40, rng)
+    x = frames(rng, 6, 40)
+    first = [list(rng.choice(40, size=4, replace=False)) for _ in range(9)]
+    second = [list(rng.choice(40, size=4, replace=False)) for _ in range(9)]
+    second[0] = first[0]  # a pair of identical torsions contributes exactly 1 and no gradient
+    cv = cvpack.TorsionSimilarity(first, second, pbc=box is not None)
+    assert cv.getName() == "torsion_similarity" and cv.getUnit().is_dimensionless()
+    run(cv, system, x, box, precision)
+
+
 def test_known_answers():
     """distance.py:37-50, angle.py:46-60, torsion.py:53-67 of the reference."""
     system = cvpack.System()

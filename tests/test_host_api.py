@@ -52,6 +52,7 @@ def all_cvs():
         cvpack.SheetRMSDContent(residues, n, blockSizes=[6, 6]),
         cvpack.PathInRMSDSpace(cvpack.path.progress, milestones, n, 0.5 * mmunit.angstroms),
         cvpack.PathInRMSDSpace(cvpack.path.deviation, milestones, n, 0.05),
+        cvpack.TorsionSimilarity([[0, 1, 2, 3], (4, 5, 6, 7)], np.array([[4, 5, 6, 7], [8, 9, 10, 11]])),
     ]
 
 
@@ -128,7 +129,7 @@ def test_yaml_tags_match_reference():
         "Angle", "AttractionStrength", "CompositeRMSD", "Distance", "HelixAngleContent",
         "HelixHBondContent", "HelixRMSDContent", "HelixTorsionContent", "NumberOfContacts",
         "PathInRMSDSpace", "RadiusOfGyration", "RadiusOfGyrationSq", "ResidueCoordination", "RMSD",
-        "SheetRMSDContent", "ShortestDistance", "Torsion",
+        "SheetRMSDContent", "ShortestDistance", "Torsion", "TorsionSimilarity",
     }
     for name in expected:
         assert getattr(cvpack, name).yaml_tag == f"!cvpack.{name}"

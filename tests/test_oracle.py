@@ -51,6 +51,22 @@ def test_torsion_sign_convention():
         assert o.torsion(x, 0, 1, 2, 3)[0] == pytest.approx(expected, rel=1e-13)
 
 
+def test_torsion_similarity():
+    """torsion_similarity.py:22-30: n/2 + 1/2 sum cos(phi1 - phi2); identical lists give n, and the
+    `min(delta, 2 pi - delta)` of the reference's expression (:89) changes neither value nor slope."""
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(12, 3))
+    first = [[0, 1, 2, 3], [2, 3, 4, 5], [6, 7, 8, 9]]
+    second = [[1, 2, 3, 4], [5, 6, 7, 8], [8, 9, 10, 11]]
+    assert o.torsion_similarity(x, first, first)[0] == pytest.approx(3.0, rel=1e-15)
+    value, _ = o.torsion_similarity(x, first, second)
+    phi1 = np.array([o.torsion(x, *t)[0] for t in first])
+    phi2 = np.array([o.torsion(x, *t)[0] for t in second])
+    assert value == pytest.approx(1.5 + 0.5 * np.cos(phi1 - phi2).sum(), rel=1e-14)
+    for box in (None, TRICLINIC):
+        fd_check(lambda y: o.torsion_similarity(y, first, second, box=box), x, range(12), tol=1e-6)
+
+
 def test_radius_of_gyration_matches_reference_test():
     """tests/test_cvpack.py:172-229: about the centroid, and about the centre of mass but unweighted."""
     rng = np.random.default_rng(1)
