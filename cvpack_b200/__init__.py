@@ -21,6 +21,7 @@ from .helix_rmsd_content import HelixRMSDContent  # noqa: F401
 from .helix_torsion_content import HelixTorsionContent  # noqa: F401
 from .mm import NonbondedForce, System, Vec3  # noqa: F401
 from .number_of_contacts import NumberOfContacts  # noqa: F401
+from .path_in_cv_space import PathInCVSpace  # noqa: F401
 from .path_in_rmsd_space import PathInRMSDSpace  # noqa: F401
 from .radius_of_gyration import RadiusOfGyration  # noqa: F401
 from .radius_of_gyration_sq import RadiusOfGyrationSq  # noqa: F401
@@ -44,6 +45,7 @@ __all__ = [
     "HelixTorsionContent",
     "NonbondedForce",
     "NumberOfContacts",
+    "PathInCVSpace",
     "PathInRMSDSpace",
     "RadiusOfGyration",
     "RadiusOfGyrationSq",

@@ -127,6 +127,20 @@ class BondedDesc(C.Structure):
     ]
 
 
+class PathCVDesc(C.Structure):
+    """``cvp_path_cv_desc``"""
+
+    _fields_ = [
+        ("num_variables", C.c_int32),
+        ("num_milestones", C.c_int32),
+        ("milestones", _f64p),
+        ("periods", _f64p),
+        ("scales", _f64p),
+        ("sigma", C.c_double),
+        ("metric", C.c_int32),
+    ]
+
+
 # every symbol include/cvpack_b200.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 _eval_args = [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int64, _vp, _vp, C.c_int]
@@ -141,6 +155,8 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     "cvp_evaluate": (C.c_int, _eval_args + [_vp]),
     "cvp_evaluate_host": (C.c_int, _eval_args + [C.c_int]),
     "cvp_effective_mass": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "cvp_path_cv_combine": (C.c_int, [C.POINTER(PathCVDesc), C.c_int, _vp, C.c_int64, _vp, _vp, _vp]),
+    "cvp_axpy_frames": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp]),
     "cvp_last_error": (C.c_char_p, []),
     "cvp_version": (C.c_int, []),
     "cvp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -310,6 +326,27 @@ class NativeCV:
 def effective_mass(dtype: int, grad: int, masses: int, num_frames: int, num_atoms: int, out: int, stream: int) -> None:
     """``cvp_effective_mass`` on device pointers."""
     check(load().cvp_effective_mass(dtype, grad, masses, num_frames, num_atoms, out, stream))
+
+
+def path_cv_combine(  # pylint: disable=too-many-arguments
+    milestones: t.Any, periods: t.Any, scales: t.Any, sigma: float, metric: int, dtype: int,
+    values: int, num_frames: int, out_value: int, out_coef: t.Optional[int], stream: int,
+) -> None:
+    """``cvp_path_cv_combine`` on device pointers (``values`` / ``out_coef``: ``[nv][B]``)."""
+    matrix = as_f64(milestones)
+    per, sca = as_f64(periods), as_f64(scales)
+    desc = PathCVDesc(
+        num_variables=matrix.shape[1], num_milestones=matrix.shape[0], milestones=ptr_f64(matrix),
+        periods=ptr_f64(per), scales=ptr_f64(sca), sigma=float(sigma), metric=int(metric),
+    )
+    check(load().cvp_path_cv_combine(C.byref(desc), dtype, values, num_frames, out_value, out_coef, stream))
+
+
+def axpy_frames(  # pylint: disable=too-many-arguments
+    dtype: int, coef: int, x: int, y: int, num_frames: int, num_atoms: int, accumulate: bool, stream: int
+) -> None:
+    """``cvp_axpy_frames`` on device pointers."""
+    check(load().cvp_axpy_frames(dtype, coef, x, y, num_frames, num_atoms, int(accumulate), stream))
 
 
 def device_info(device: int = 0) -> t.Tuple[int, int, int]:

@@ -222,6 +222,15 @@ class BatchContext:
         out: t.Optional[t.Tuple[torch.Tensor, t.Optional[torch.Tensor]]] = None,
     ) -> t.Tuple[torch.Tensor, t.Optional[torch.Tensor]]:
         self._require_cuda()
+        if hasattr(cv, "_evaluateComposite"):
+            # a variable defined on other variables (PathInCVSpace): no single kernel spec
+            if out is not None:
+                pos = self.getPositions() if positions is None else positions
+                self._check_out(
+                    out, int(pos.shape[0]), int(pos.shape[1]), need_gradient,
+                    self._residency == "host" and positions is None,
+                )
+            return cv._evaluateComposite(self, need_gradient, positions, out)
         pos = self.getPositions() if positions is None else positions
         num_frames, num_atoms = int(pos.shape[0]), int(pos.shape[1])
         native = self._native_cv(cv)

@@ -212,6 +212,29 @@ int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* 
 int cvp_effective_mass(int dtype, const void* grad, const double* masses, int64_t num_frames,
                        int64_t num_atoms, void* emass, void* stream);
 
+/* ---- PathInCVSpace: a path of milestones in the space of other collective variables ----------- */
+/* Replaces the CustomCVForce expression assembled by path_in_cv_space.py:141-158 and
+ * base_path_cv.py:43-62.  The inner CVs are evaluated with cvp_evaluate; this entry combines their
+ * values [num_variables][B] (device, coordinate type) into the path value [B] and the partial
+ * derivatives d value / d cv_j [num_variables][B] (`out_coef`, may be NULL); cvp_axpy_frames then
+ * accumulates coef_j[b] * gradient_j[b][N][3] into the gradient of the path variable.             */
+typedef struct {
+  int32_t num_variables;
+  int32_t num_milestones;         /* >= 2                                                          */
+  const double* milestones;       /* [num_milestones][num_variables], MD units                     */
+  const double* periods;          /* [num_variables]; 0 = not periodic, else upper - lower bound   */
+  const double* scales;           /* [num_variables] characteristic scales (> 0)                   */
+  double sigma;                   /* width of the Gaussian kernels                                 */
+  int32_t metric;                 /* CVP_COMBINE_PATH_PROGRESS or CVP_COMBINE_PATH_DEVIATION       */
+} cvp_path_cv_desc;
+
+int cvp_path_cv_combine(const cvp_path_cv_desc* desc, int dtype, const void* values,
+                        int64_t num_frames, void* out_value, void* out_coef, void* stream);
+
+/* y[b][N][3] = (accumulate ? y : 0) + coef[b] * x[b][N][3]; device buffers of the given dtype.   */
+int cvp_axpy_frames(int dtype, const void* coef, const void* x, void* y, int64_t num_frames,
+                    int64_t num_atoms, int accumulate, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------- */
 const char* cvp_last_error(void);
 int cvp_version(void);

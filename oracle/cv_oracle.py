@@ -171,6 +171,60 @@ def torsion_similarity(
     return total, grad
 
 
+def path_in_cv_space(
+    values: t.Sequence[float],
+    gradients: t.Sequence[np.ndarray],
+    milestones: np.ndarray,
+    sigma: float,
+    metric: str,
+    periods: t.Optional[t.Sequence[float]] = None,
+    scales: t.Optional[t.Sequence[float]] = None,
+):
+    """
+    Progress / deviation along a path of milestones in the space of other CVs, from the inner CVs'
+    values and gradients (path_in_cv_space.py:141-158 + base_path_cv.py:43-62):
+    x_i = sum_j (delta_ij/scale_j)^2 with delta = m_ij - cv_j, or min(|delta|, P - |delta|) for a
+    periodic variable (Lepton: min() differentiates the branch taken, the second on ties;
+    abs'(0) = +1); w_i = exp(lambda (xmin - x_i)), lambda = 1/(2 sigma^2);
+    s = sum_i i w_i/((n-1) sum w), z = xmin - ln(sum w)/lambda.
+    """
+    milestones = np.atleast_2d(np.asarray(milestones, dtype=float))
+    n, nv = milestones.shape
+    periods = [0.0] * nv if periods is None else list(periods)
+    scales = [1.0] * nv if scales is None else list(scales)
+    lam = 1.0 / (2.0 * sigma * sigma)
+    x = np.zeros(n)
+    dx = np.zeros((n, nv))  # d x_i / d cv_j
+    for i in range(n):
+        for j in range(nv):
+            delta = milestones[i, j] - values[j]
+            if periods[j] > 0:
+                a = abs(delta)
+                sign = 1.0 if delta >= 0 else -1.0
+                if a < periods[j] - a:
+                    m, dm = a, -sign
+                else:
+                    m, dm = periods[j] - a, sign
+            else:
+                m, dm = delta, -1.0
+            x[i] += (m / scales[j]) ** 2
+            dx[i, j] = 2.0 * m * dm / scales[j] ** 2
+    xmin = x.min()
+    w = np.exp(lam * (xmin - x))
+    wsum = w.sum()
+    index = np.arange(n)
+    s = (index * w).sum() / ((n - 1) * wsum)
+    if metric == "progress":
+        value = s
+        dvalue = -lam * w * (index / (n - 1) - s) / wsum
+    else:
+        value = xmin - np.log(wsum) / lam
+        dvalue = w / wsum
+    coef = dvalue @ dx
+    grad = sum(c * g for c, g in zip(coef, gradients))
+    return value, grad
+
+
 def bonded_sum(
     x: np.ndarray,
     terms: t.Sequence[t.Sequence[int]],

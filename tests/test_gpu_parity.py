@@ -12,6 +12,7 @@ import io
 
 import numpy as np
 import pytest
+import torch
 
 import cvpack_b200 as cvpack
 from cvpack_b200 import mmunit, serialization
@@ -60,6 +61,29 @@ def test_torsion_similarity(precision, boxname):
     cv = cvpack.TorsionSimilarity(first, second, pbc=box is not None)
     assert cv.getName() == "torsion_similarity" and cv.getUnit().is_dimensionless()
     run(cv, system, x, box, precision)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("metric", ["progress", "deviation"])
+def test_path_in_cv_space(precision, metric):
+    """Torsion (periodic) x Distance x RadiusOfGyration space, scaled; the inner variables run their
+    own kernels and the combination applies the chain rule (path_in_cv_space.py:141-158)."""
+    rng = np.random.default_rng(13)
+    system = helpers.make_system(30, rng)
+    x = frames(rng, 7, 30, scale=1.5)
+    variables = [cvpack.Torsion(3, 17, 5, 9), cvpack.Distance(2, 11), cvpack.RadiusOfGyration(range(8, 20))]
+    milestones = np.array([[3.0, 0.4, 0.5], [-3.0, 0.8, 0.6], [-2.0, 1.2, 0.7], [0.5, 1.6, 0.8], [1.5, 2.0, 0.9]])
+    cv = cvpack.PathInCVSpace(getattr(cvpack.path, metric), variables, milestones, 0.8,
+                              scales=[1.0, 0.5 * mmunit.nanometers, 0.2])
+    assert cv.getName() == f"path_{metric}_in_cv_space" and cv.getUnit().is_dimensionless()
+    vt, gt = TOL[precision]
+    ctx = helpers.check_against_oracle(cv, system, x, None, precision, 5 * vt, 5 * gt)
+    emass = cv.getEffectiveMass(ctx)
+    assert torch.isfinite(emass._value).all()  # pylint: disable=protected-access
+    with pytest.raises(ValueError, match="Wrong number of columns"):
+        cvpack.PathInCVSpace(cvpack.path.progress, variables, milestones[:, :2], 0.8)
+    with pytest.raises(ValueError, match="At least two rows"):
+        cvpack.PathInCVSpace(cvpack.path.progress, variables, milestones[:1], 0.8)
 
 
 def test_known_answers():
@@ -397,3 +421,53 @@ def test_host_residency_matches_device():
     assert not v2._value.is_cuda and not g2.is_cuda
     assert bool((v1._value.cpu() == v2._value).all())
     assert bool((g1.cpu() == g2).all())
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_config0_solvated_dipeptide_single_frame(precision):
+    """BASELINE.json configs[0] (openmmtools AlanineDipeptideExplicit, 2269 atoms, single frame:
+    Distance, Torsion, RadiusOfGyration, RMSD, NumberOfContacts).  openmmtools' coordinates are not
+    available offline, so the frame is the synthetic stand-in SURVEY 8(d) specifies:
+    a 22-atom solute chain plus 749 three-site waters on a jittered lattice, seed 1, cubic box."""
+    rng = np.random.default_rng(1)
+    box_length = 2.84
+    solute = [np.full(3, 0.5 * box_length)]
+    for _ in range(21):
+        step = rng.normal(size=3)
+        solute.append(solute[-1] + 0.15 * step / np.linalg.norm(step))
+    m = 10
+    grid = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    sites = (grid[rng.permutation(m**3)[:749]] + 0.5) * (box_length / m)
+    sites = sites + 0.03 * rng.normal(size=sites.shape)
+    waters = []
+    for oxygen in sites:
+        waters.append(oxygen)
+        for _ in range(2):
+            h = rng.normal(size=3)
+            waters.append(oxygen + 0.1 * h / np.linalg.norm(h))
+    x = np.concatenate([np.array(solute), np.array(waters)])
+    n = x.shape[0]
+    assert n == 2269
+    system = helpers.make_system(n, rng)
+    box = np.diag([box_length] * 3)
+    nb = helpers.make_nonbonded(n, rng, periodic=True, cutoff=0.9)
+    reference = x[:22] + 0.02 * rng.normal(size=(22, 3))
+    oxygens = range(22, n, 3)
+    cvs = [
+        cvpack.Distance(0, 21),
+        cvpack.Torsion(4, 6, 8, 14),   # phi of alanine dipeptide
+        cvpack.Torsion(6, 8, 14, 16),  # psi
+        cvpack.RadiusOfGyration(range(22)),
+        cvpack.RMSD({i: reference[i] for i in range(22)}, range(22), n),
+        cvpack.NumberOfContacts(range(22), oxygens, nb, thresholdDistance=0.3),
+    ]
+    ctx = None
+    for cv in cvs:
+        cv.addToSystem(system)
+    for cv in cvs:
+        vt, gt = TOL[precision]
+        if ctx is None:
+            ctx = cvpack.BatchContext(system, x[None], box, precision=precision)
+        helpers.check_against_oracle(cv, system, x[None], box, precision, vt, gt, context=ctx)
+    emass = cvs[3].getEffectiveMass(ctx)
+    assert np.isfinite(float(emass._value[0])) and float(emass._value[0]) > 0  # pylint: disable=protected-access

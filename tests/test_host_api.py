@@ -53,6 +53,14 @@ def all_cvs():
         cvpack.PathInRMSDSpace(cvpack.path.progress, milestones, n, 0.5 * mmunit.angstroms),
         cvpack.PathInRMSDSpace(cvpack.path.deviation, milestones, n, 0.05),
         cvpack.TorsionSimilarity([[0, 1, 2, 3], (4, 5, 6, 7)], np.array([[4, 5, 6, 7], [8, 9, 10, 11]])),
+        cvpack.PathInCVSpace(
+            cvpack.path.progress, [cvpack.Torsion(0, 1, 2, 3), cvpack.Distance(0, 5)],
+            [[1.3, 0.2], [1.2, 0.4], [-2.7, 0.5]], np.pi / 6, scales=[1.0, 0.1],
+        ),
+        cvpack.PathInCVSpace(
+            cvpack.path.deviation, [cvpack.Torsion(0, 1, 2, 3), cvpack.Torsion(1, 2, 3, 4)],
+            [[1.3, -0.2], [1.2, 3.1]], 0.5,
+        ),
     ]
 
 
@@ -129,7 +137,7 @@ def test_yaml_tags_match_reference():
         "Angle", "AttractionStrength", "CompositeRMSD", "Distance", "HelixAngleContent",
         "HelixHBondContent", "HelixRMSDContent", "HelixTorsionContent", "NumberOfContacts",
         "PathInRMSDSpace", "RadiusOfGyration", "RadiusOfGyrationSq", "ResidueCoordination", "RMSD",
-        "SheetRMSDContent", "ShortestDistance", "Torsion", "TorsionSimilarity",
+        "SheetRMSDContent", "ShortestDistance", "Torsion", "TorsionSimilarity", "PathInCVSpace",
     }
     for name in expected:
         assert getattr(cvpack, name).yaml_tag == f"!cvpack.{name}"

@@ -67,6 +67,34 @@ def test_torsion_similarity():
         fd_check(lambda y: o.torsion_similarity(y, first, second, box=box), x, range(12), tol=1e-6)
 
 
+def test_path_in_cv_space_matches_logsumexp_and_finite_differences():
+    """The softmin forms the reference's test-suite uses for the path CVs
+    (tests/test_cvpack.py:807-860) applied to a path in (torsion, distance) space, with the
+    periodic difference of path_in_cv_space.py:148-149; gradient by finite differences."""
+    from scipy.special import logsumexp, softmax
+
+    rng = np.random.default_rng(6)
+    x = rng.normal(size=(6, 3))
+    milestones = np.array([[3.0, 0.5], [-3.0, 1.0], [-2.0, 1.5], [0.5, 2.0]])
+    sigma, periods, scales = 0.7, [2 * np.pi, 0.0], [1.0, 0.5]
+
+    def evaluate(y, metric):
+        inner = [o.torsion(y, 0, 1, 2, 3), o.distance(y, 1, 4)]
+        return o.path_in_cv_space([v for v, _ in inner], [g for _, g in inner], milestones, sigma,
+                                  metric, periods, scales)
+
+    phi, dist = o.torsion(x, 0, 1, 2, 3)[0], o.distance(x, 1, 4)[0]
+    dphi = np.abs(milestones[:, 0] - phi)
+    dphi = np.minimum(dphi, 2 * np.pi - dphi)
+    sq = dphi**2 + ((milestones[:, 1] - dist) / 0.5) ** 2
+    exponents = -sq / (2 * sigma**2)
+    assert evaluate(x, "progress")[0] == pytest.approx(
+        np.dot(softmax(exponents), np.arange(4)) / 3, rel=1e-12)
+    assert evaluate(x, "deviation")[0] == pytest.approx(-2 * sigma**2 * logsumexp(exponents), rel=1e-12)
+    for metric in ("progress", "deviation"):
+        fd_check(lambda y, metric=metric: evaluate(y, metric), x, range(6), tol=1e-6)
+
+
 def test_radius_of_gyration_matches_reference_test():
     """tests/test_cvpack.py:172-229: about the centroid, and about the centre of mass but unweighted."""
     rng = np.random.default_rng(1)
