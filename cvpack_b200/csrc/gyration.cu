@@ -316,6 +316,7 @@ struct GyrationFusedPolicy {
   static constexpr int NS = WEIGHTED ? 7 : 4;
   static constexpr int AUX = WEIGHTED ? 1 : 0;
   static constexpr int AUXD = 0;
+  static constexpr int FRAME_FLOATS = 7;
   struct Params {
     int n;
     int squared;

@@ -318,6 +318,7 @@ struct RmsdFusedPolicy {
   static constexpr int NS = 13;
   static constexpr int AUX = 3;   // per-atom auxiliary data: the centred reference, float [n][3]
   static constexpr int AUXD = 3;  // ... and the same values as doubles for the sums
+  static constexpr int FRAME_FLOATS = 13;
   struct Params {
     double gy;  // sum |y^|^2 of that reference
     int n;

@@ -25,14 +25,14 @@
 //     extra *solver warp* per CTA owns the frames f = cta, cta + #CTAs, ...: it reads the records
 //     of the frame's SS sub-slices, re-reading those whose tags have not arrived, adds them in
 //     slice order (deterministic), runs the per-frame solve in one lane and publishes the frame
-//     constants with a release flag.  (Letting the last streaming warp solve
+//     constants the same way, as tagged records {c0, tag, c1, tag}: no fence, no flag.  (Letting the last streaming warp solve
 //     puts the solve on the critical path of that warp's frame class: it is late for the next
 //     frame, hence last again, and ends up solving every frame of the class serially.)
-//   * GRAD(f) needs that flag.  SUM items never wait and the schedule is static, so the flag a warp
-//     waits for only depends on iterations < t of other warps: no deadlock as long as all CTAs are
-//     co-resident, which the cooperative launch guarantees.  The flag and the constants of the
-//     GRAD item are fetched at the start of the SUM item that precedes it, so in the steady state
-//     nobody waits.
+//   * GRAD(f) needs those constants.  SUM items never wait and the schedule is static, so the
+//     records a warp waits for only depend on iterations < t of other warps: no deadlock as long as
+//     all CTAs are co-resident, which the cooperative launch guarantees.  The constants of the GRAD
+//     item are fetched at the start of the SUM item that precedes it (one L2 round trip, checked
+//     when needed), so in the steady state nobody waits.
 #pragma once
 
 #include <cooperative_groups.h>
@@ -184,7 +184,8 @@ struct FusedGeom {
 //                                              3): the same values, pre-converted, in the
 //                                              conflict-free layout of fused_permute_doubles()
 //   struct Params                              per-launch constants
-//   struct Frame                               per-frame constants of the gradient; 64 bytes
+//   struct Frame                               per-frame constants of the gradient; 64 bytes, of
+//   static constexpr int FRAME_FLOATS          which the first FRAME_FLOATS floats are used
 //   accumulate(params, aux, auxd, x, y, z, v)  add 4 atoms to the sums; aux = this lane's 4*AUX
 //                                              floats in shared memory, auxd = its first double2
 //                                              (the others follow at strides of 32 double2)
@@ -208,8 +209,8 @@ template <typename Policy>
 __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
     stream_fused_kernel(const float* __restrict__ pos, const float* __restrict__ aux_global,
                         const double* __restrict__ auxd_global, FusedGeom geom, typename Policy::Params params,
-                        int* __restrict__ ready, uint4* __restrict__ partials,
-                        typename Policy::Frame* __restrict__ frames, float* __restrict__ value,
+                        uint4* __restrict__ partials, uint4* __restrict__ frames /* tagged */,
+                        float* __restrict__ value,
                         float* __restrict__ grad, int accumulate) {
   using Layout = FusedLayout<Policy>;
   constexpr int NS = Policy::NS;
@@ -218,6 +219,8 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
   constexpr int CH = FUSED_CHUNK_BYTES;
   static_assert(FUSED_STAGES == 2, "the ring logic below assumes two stages");
   static_assert(sizeof(typename Policy::Frame) == 64, "Frame must be 64 bytes");
+  // frame constants travel as FREC records {c[2k], tag, c[2k+1], tag}
+  constexpr int FREC = (Policy::FRAME_FLOATS + 1) / 2;
   static_assert(NS <= 16, "at most 16 sums");
   extern __shared__ __align__(128) unsigned char fused_smem[];
   __shared__ uint64_t s_aux_bar[FUSED_MAX_WARPS];
@@ -275,9 +278,12 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 #pragma unroll
       for (int k = 0; k < NS; ++k) sums[k] = warp_sum(sums[k]);
       if (lane == 0) {
-        Policy::complete(params, sums, frames + frame + 1, value + frame, accumulate);
-        __threadfence();
-        st_release_gpu(ready + frame, 1);
+        typename Policy::Frame fr;
+        Policy::complete(params, sums, &fr, value + frame, accumulate);
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(&fr);
+#pragma unroll
+        for (int k = 0; k < FREC; ++k)
+          st_relaxed_gpu_v4(frames + frame * FREC + k, make_uint4(words[2 * k], 1u, words[2 * k + 1], 1u));
       }
       __syncwarp();
     }
@@ -357,20 +363,15 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
   const float* lane_aux = s_aux + lane * 4 * AUX;
   const double2* lane_auxd = reinterpret_cast<const double2*>(s_auxd) + lane;
 
-  // frame constants of the next GRAD item, fetched early
-  int pre_flag = 0;
-  float4 pre[4];
+  // frame constants of the next GRAD item, fetched early (valid once every record carries tag 1)
+  uint4 pre[FREC];
 
   for (int t = 0; t < t_end; ++t) {
     const bool grad_valid = job_valid(t, 1);
     const int64_t grad_frame = (int64_t)(t - L) * RR + r;
     if (grad_valid) {
-      pre_flag = ld_relaxed_gpu(ready + grad_frame);
-      // slot 0 is a dummy: the address depends on the flag, so the loads cannot pass it
-      const float4* src =
-          reinterpret_cast<const float4*>(frames + (pre_flag != 0 ? grad_frame + 1 : 0));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pre[k] = __ldcg(src + k);
+      for (int k = 0; k < FREC; ++k) pre[k] = ld_relaxed_gpu_v4(frames + grad_frame * FREC + k);
     }
 
     if (job_valid(t, 0)) {
@@ -429,21 +430,23 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 
     if (grad_valid) {
       // ---- GRAD ----------------------------------------------------------------------------------
-      if (!__all_sync(0xffffffffu, pre_flag != 0)) {
-        if (lane == 0) {
-          while (ld_relaxed_gpu(ready + grad_frame) == 0) __nanosleep(256);
-        }
-        __syncwarp();
-        (void)ld_acquire_gpu(ready + grad_frame);
-        const float4* src = reinterpret_cast<const float4*>(frames + grad_frame + 1);
+      for (;;) {
+        bool valid = true;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pre[k] = __ldcg(src + k);
+        for (int k = 0; k < FREC; ++k) valid = valid && pre[k].y == 1u && pre[k].w == 1u;
+        if (__all_sync(0xffffffffu, valid)) break;
+        __nanosleep(200);
+#pragma unroll
+        for (int k = 0; k < FREC; ++k) pre[k] = ld_relaxed_gpu_v4(frames + grad_frame * FREC + k);
       }
       typename Policy::Frame fr;
       {
-        float4* dst = reinterpret_cast<float4*>(&fr);
+        uint32_t* words = reinterpret_cast<uint32_t*>(&fr);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = pre[k];
+        for (int k = 0; k < FREC; ++k) {
+          words[2 * k] = pre[k].x;
+          if (2 * k + 1 < Policy::FRAME_FLOATS) words[2 * k + 1] = pre[k].z;
+        }
       }
       float* gdst = grad + grad_frame * frame_stride + ((int64_t)geom.first_atom + a0) * 3;
       int left = ng;
@@ -495,12 +498,11 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 template <typename Policy>
 struct FusedLaunch {
   using Layout = FusedLayout<Policy>;
-  // workspace: ready[B], frames[B + 1], partial records[B * SS_max * NS]; SS_max for the smallest
+  // workspace: tagged frame constants[B], partial records[B * SS_max * NS]; SS_max for the smallest
   // sub-slice
   static size_t workspace_per_frame(int n) {
     const size_t ss_max = (size_t)div_up(n, FUSED_CHUNK_ATOMS);
-    return ss_max * Policy::NS * sizeof(uint4) + sizeof(typename Policy::Frame) + 2 * sizeof(int) +
-           16;
+    return ss_max * Policy::NS * sizeof(uint4) + 2 * sizeof(typename Policy::Frame) + 16;
   }
   static size_t workspace_fixed() { return 8 * 256 + sizeof(typename Policy::Frame); }
 
@@ -574,13 +576,13 @@ struct FusedLaunch {
     using Frame = typename Policy::Frame;
     const size_t B = (size_t)geom.num_frames;
     Carver carve(workspace);
-    int* ready = carve.take<int>(B);
-    Frame* frames = carve.take<Frame>(B + 1);
+    constexpr size_t FREC = (Policy::FRAME_FLOATS + 1) / 2;
+    uint4* frames = carve.take<uint4>(B * FREC);  // tagged frame constants (tag 0 = not yet solved)
     const size_t record_frames =
         geom.ring_rounds < geom.T ? (size_t)geom.ring_rounds * geom.RR : B;  // (ring: < B frames)
     const size_t records = record_frames * geom.SS * Policy::NS;
     uint4* partials = carve.take<uint4>(records);
-    CVP_CUDA_CHECK(cudaMemsetAsync(ready, 0, B * sizeof(int), stream));
+    CVP_CUDA_CHECK(cudaMemsetAsync(frames, 0, B * FREC * sizeof(uint4), stream));
     CVP_CUDA_CHECK(cudaMemsetAsync(partials, 0, records * sizeof(uint4), stream));  // tag 0 = empty
     const size_t smem = (size_t)geom.slots * Layout::slot_bytes(geom.sub) +
                         (size_t)geom.warps_per_cta * Layout::WARP_BYTES;
@@ -596,7 +598,7 @@ struct FusedLaunch {
     FusedGeom g = geom;
     typename Policy::Params p = params;
     int acc = accumulate ? 1 : 0;
-    void* args[] = {(void*)&pos, (void*)&aux, (void*)&auxd, (void*)&g, (void*)&p, (void*)&ready,
+    void* args[] = {(void*)&pos, (void*)&aux, (void*)&auxd, (void*)&g, (void*)&p,
                     (void*)&partials, (void*)&frames, (void*)&value, (void*)&grad, (void*)&acc};
     // cooperative: all CTAs are guaranteed to be co-resident (GRAD items wait for other CTAs)
     CVP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)stream_fused_kernel<Policy>, dim3(blocks),
