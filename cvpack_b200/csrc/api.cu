@@ -266,6 +266,7 @@ int cvp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
 
 int64_t cvp_launch_count(void) { return g_launch_count.load(); }
 
+
 int cvp_set_workspace_limit(cvp_cv* cv, int64_t bytes) {
   CVP_REQUIRE(cv != nullptr && bytes > 0, "bad workspace limit");
   cv->workspace_limit = bytes;

@@ -94,12 +94,15 @@ __device__ __forceinline__ void unpack4(const float4& a0, const float4& a1, cons
 
 __global__ void __launch_bounds__(RMSD_FAST_THREADS)
     rmsd_sums_fast_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom, int n,
-                          const float* __restrict__ ref, int nslice, double* __restrict__ partials) {
+                          const double* __restrict__ ref, int nslice, double* __restrict__ partials) {
   __shared__ double scratch[13 * (RMSD_FAST_THREADS / 32)];
   const int64_t b = blockIdx.x / nslice;
   const int s = blockIdx.x - (int)b * nslice;
   const float4* px = reinterpret_cast<const float4*>(pos + (b * num_atoms + first_atom) * 3);
-  const float4* py = reinterpret_cast<const float4*>(ref);
+  // the centred reference in double: rounded to float it is no longer centred, and the
+  // single-pass covariance sum x (x) y^ (x not centred) picks up c (x) sum y^ -- an error of 1e-9 in
+  // the mean square deviation, i.e. of 5e-5 nm in an RMSD close to zero
+  const double2* py = reinterpret_cast<const double2*>(ref);
   const int g_begin = s * (RMSD_FAST_SLICE / 4);
   const int g_end = min(n / 4, g_begin + RMSD_FAST_SLICE / 4);
   double v[13];
@@ -107,10 +110,14 @@ __global__ void __launch_bounds__(RMSD_FAST_THREADS)
   for (int k = 0; k < 13; ++k) v[k] = 0.0;
   for (int g = g_begin + threadIdx.x; g < g_end; g += RMSD_FAST_THREADS) {
     const float4 a0 = __ldg(px + 3 * g), a1 = __ldg(px + 3 * g + 1), a2 = __ldg(px + 3 * g + 2);
-    const float4 r0 = __ldg(py + 3 * g), r1 = __ldg(py + 3 * g + 1), r2 = __ldg(py + 3 * g + 2);
-    float x[4], y[4], z[4], rx[4], ry[4], rz[4];
+    double2 r[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r[k] = __ldg(py + 6 * g + k);
+    const double rx[4] = {r[0].x, r[1].y, r[3].x, r[4].y};
+    const double ry[4] = {r[0].y, r[2].x, r[3].y, r[5].x};
+    const double rz[4] = {r[1].x, r[2].y, r[4].x, r[5].y};
+    float x[4], y[4], z[4];
     unpack4(a0, a1, a2, x, y, z);
-    unpack4(r0, r1, r2, rx, ry, rz);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const double xd = x[k], yd = y[k], zd = z[k], rxd = rx[k], ryd = ry[k], rzd = rz[k];
@@ -317,7 +324,7 @@ __device__ inline void rmsd_from_sums(const double* sums, double gy, int n, bool
 struct RmsdFusedPolicy {
   static constexpr int NS = 13;
   static constexpr int AUX = 3;   // per-atom auxiliary data: the centred reference, float [n][3]
-  static constexpr int AUXD = 3;  // ... and the same values as doubles for the sums
+  static constexpr int AUXD = 3;  // ... and in double for the sums (exactly centred)
   static constexpr int FRAME_FLOATS = 13;
   struct Params {
     double gy;  // sum |y^|^2 of that reference
@@ -629,9 +636,8 @@ struct RmsdCV : cvp_cv {
   int multi_first = 0, multi_n = 0, multi_sk_max = 1;
   std::vector<float> ref_f32;
   std::vector<int32_t> fast_seg_slice_offsets;
-  std::vector<double> fast_gy;
-  DeviceBuffer d_ref_f32, d_ref_perm, d_fast_seg_slice_offsets, d_fast_gy;
-  std::vector<double> ref_perm;  // ref_f32 as doubles in the layout of fused_permute_doubles()
+  DeviceBuffer d_ref_f32, d_ref_perm, d_fast_seg_slice_offsets;
+  std::vector<double> ref_perm;  // the centred reference in the layout of fused_permute_doubles()
   int num_groups = 0, nseg = 0, nslice = 0;
   int64_t num_entries = 0;
   CombineParams cp{};
@@ -650,7 +656,7 @@ struct RmsdCV : cvp_cv {
     for (DeviceBuffer* buf :
          {&d_entry_atom, &d_entry_group, &d_entry_seg, &d_ref, &d_slices, &d_group_seg_offsets,
           &d_seg_slice_offsets, &d_seg_size, &d_group_size, &d_group_gy, &d_active,
-          &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_ref_perm, &d_fast_seg_slice_offsets, &d_fast_gy})
+          &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_ref_perm, &d_fast_seg_slice_offsets})
       buf->release();
   }
   int upload() override {
@@ -673,7 +679,6 @@ struct RmsdCV : cvp_cv {
     CVP_UP(d_ref_f32, ref_f32);
     CVP_UP(d_ref_perm, ref_perm);
     CVP_UP(d_fast_seg_slice_offsets, fast_seg_slice_offsets);
-    CVP_UP(d_fast_gy, fast_gy);
 #undef CVP_UP
     return CVP_OK;
   }
@@ -739,7 +744,7 @@ struct RmsdCV : cvp_cv {
         FusedLaunch<RmsdFusedPolicy>::plan((int)num_entries, N, fast_first, B, grad != nullptr,
                                            fused_lag, fused_slice, fused_slots, fused_hints, sm_count(), &geom)) {
       RmsdFusedPolicy::Params params;
-      params.gy = fast_gy[0];
+      params.gy = group_gy[0];
       params.n = (int)num_entries;
       if (grad != nullptr && !accumulate && !dense)
         CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
@@ -805,7 +810,7 @@ struct RmsdCV : cvp_cv {
       timer.begin("rmsd_sums", st);
       rmsd_sums_fast_kernel<<<(unsigned)(B * ns), RMSD_FAST_THREADS, 0, st>>>(
           reinterpret_cast<const float*>(pos), N, fast_first, (int)num_entries,
-          static_cast<const float*>(d_ref_f32.ptr), ns, partials);
+          static_cast<const double*>(d_ref.ptr), ns, partials);
       timer.end(st);
       CVP_LAUNCH_CHECK();
     } else {
@@ -827,7 +832,7 @@ struct RmsdCV : cvp_cv {
                                                : d_seg_slice_offsets.ptr),
           static_cast<const int32_t*>(d_seg_size.ptr),
           static_cast<const int32_t*>(d_group_size.ptr),
-          static_cast<const double*>(use_fast ? d_fast_gy.ptr : d_group_gy.ptr), num_groups, B,
+          static_cast<const double*>(d_group_gy.ptr), num_groups, B,
           solution, seg_centroid, nseg);
       timer.end(st);
       CVP_LAUNCH_CHECK();
@@ -985,14 +990,11 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
       cv->fast = true;
       cv->fast_first = cv->entry_atom[0];
       cv->fast_nslice = (int)div_up(E, RMSD_FAST_SLICE);
+      // the sums use the centred reference in double (see rmsd_sums_fast_kernel), the FP32
+      // gradient its float copy
       cv->ref_f32.resize((size_t)E * 3);
-      double gy = 0.0;
-      for (size_t k = 0; k < cv->ref_f32.size(); ++k) {
-        cv->ref_f32[k] = (float)cv->ref[k];
-        gy += (double)cv->ref_f32[k] * (double)cv->ref_f32[k];
-      }
-      cv->fast_gy.assign(1, gy);
-      cv->ref_perm = fused_permute_doubles(cv->ref_f32.data(), (size_t)E);
+      for (size_t k = 0; k < cv->ref_f32.size(); ++k) cv->ref_f32[k] = (float)cv->ref[k];
+      cv->ref_perm = fused_permute_doubles(cv->ref.data(), (size_t)E);
       cv->fast_seg_slice_offsets = {0, cv->fast_nslice};
     }
   }
@@ -1018,3 +1020,13 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
 }
 
 }  // namespace cvp
+
+#ifdef FUSED_TIMING
+// diagnostics build only (make EXTRA=-DFUSED_TIMING): where the RMSD instantiation of
+// stream_fused_kernel writes its per-frame timestamps ([frames][6] unsigned long long, device memory
+// owned by the caller; scripts/fused_timing.py)
+extern "C" int cvp_debug_set_fused_timing(void* device_buffer) {
+  CVP_CUDA_CHECK(cudaMemcpyToSymbol(cvp::g_fused_timing, &device_buffer, sizeof(void*)));
+  return CVP_OK;
+}
+#endif

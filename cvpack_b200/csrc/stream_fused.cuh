@@ -125,6 +125,16 @@ __device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint4* p) {
                : "memory");
   return v;
 }
+// L2-only (cache-global) load for polling tagged records: never served by a stale L1 line, and
+// unlike the .relaxed.gpu form it pipelines like an ordinary load
+__device__ __forceinline__ uint4 ld_cg_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_relaxed_gpu_v4(uint4* p, const uint4& v) {
   asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)
@@ -149,7 +159,8 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 // groups of 4 atoms = 6 double2 per group; piece j of group l of a block sits at double2 index
 // j * 32 + l, so that a warp reads one piece with a conflict-free LDS.128.  The array is padded
 // with zeros to a whole number of blocks.
-inline std::vector<double> fused_permute_doubles(const float* values, size_t atoms) {
+template <typename V>
+inline std::vector<double> fused_permute_doubles(const V* values, size_t atoms) {
   const size_t blocks = (atoms + 127) / 128;
   std::vector<double> out(blocks * 128 * 3, 0.0);
   for (size_t a = 0; a < atoms; ++a)
@@ -159,6 +170,18 @@ inline std::vector<double> fused_permute_doubles(const float* values, size_t ato
     }
   return out;
 }
+
+#ifdef FUSED_TIMING
+// (diagnostics build) per-frame timestamps in nanoseconds: [frame][6] =
+// first record written, last record written, records gathered, constants published,
+// first consumer needs the constants, last consumer has them
+static __device__ unsigned long long* g_fused_timing = nullptr;  // (one copy per translation unit)
+__device__ __forceinline__ unsigned long long fused_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
 
 // Geometry of a launch (host-chosen, see FusedLaunch::plan).
 struct FusedGeom {
@@ -253,8 +276,20 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 
   if (warp == wpc) {
     // ---- solver warp: frames blockIdx.x, blockIdx.x + gridDim.x, ... ------------------------------
-    for (int64_t frame = blockIdx.x; frame < B; frame += gridDim.x) {
-      const int round = (int)(frame / RR);
+    // Solvers are dedicated to frame classes (solver c serves class c % RR, every M-th round of
+    // it): within a class frames complete in order, so a solver never sits on a frame of a slow
+    // class while later frames of faster classes are ready (measured: 20-50 us of head-of-line
+    // blocking with a round-robin assignment).
+    const int M = max(1, (int)gridDim.x / RR);  // solvers per class
+    const int solver_class = blockIdx.x % RR, solver_phase = blockIdx.x / RR;
+    // with fewer CTAs than classes a solver takes several classes, round by round
+    const int class_stride = gridDim.x < (unsigned)RR ? (int)gridDim.x : RR;
+    if (gridDim.x >= (unsigned)RR && solver_phase >= M) return;
+    for (int round = gridDim.x >= (unsigned)RR ? solver_phase : 0; round < T;
+         round += gridDim.x >= (unsigned)RR ? M : 1)
+    for (int cls = solver_class; cls < RR; cls += class_stride) {
+      const int64_t frame = (int64_t)round * RR + cls;
+      if (frame >= B) continue;
       const uint32_t tag = (uint32_t)round + 1u;
       const int64_t slot = use_ring ? (int64_t)(round % geom.ring_rounds) * RR + frame % RR : frame;
       double sums[NS];
@@ -263,20 +298,26 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
       const uint4* in = partials + slot * SS * NS;
       for (int q = lane; q < SS; q += 32) {
         const uint4* rec = in + (size_t)q * NS;
+        // one batch of NS independent L2 loads per attempt (re-reading a record at a time costs a
+        // round trip per late record, and volatile loads end up interleaved with their own checks)
         uint4 v[NS];
+        for (;;) {
 #pragma unroll
-        for (int k = 0; k < NS; ++k) v[k] = ld_relaxed_gpu_v4(rec + k);
+          for (int k = 0; k < NS; ++k) v[k] = ld_cg_v4(rec + k);
+          bool valid = true;
 #pragma unroll
-        for (int k = 0; k < NS; ++k) {
-          while (v[k].y != tag || v[k].w != tag) {
-            __nanosleep(100);
-            v[k] = ld_relaxed_gpu_v4(rec + k);
-          }
-          sums[k] += __hiloint2double((int)v[k].z, (int)v[k].x);
+          for (int k = 0; k < NS; ++k) valid = valid && v[k].y == tag && v[k].w == tag;
+          if (valid) break;
+          __nanosleep(100);
         }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) sums[k] += __hiloint2double((int)v[k].z, (int)v[k].x);
       }
 #pragma unroll
       for (int k = 0; k < NS; ++k) sums[k] = warp_sum(sums[k]);
+#ifdef FUSED_TIMING
+      if (lane == 0 && g_fused_timing != nullptr) g_fused_timing[frame * 6 + 2] = fused_now();
+#endif
       if (lane == 0) {
         typename Policy::Frame fr;
         Policy::complete(params, sums, &fr, value + frame, accumulate);
@@ -284,6 +325,9 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 #pragma unroll
         for (int k = 0; k < FREC; ++k)
           st_relaxed_gpu_v4(frames + frame * FREC + k, make_uint4(words[2 * k], 1u, words[2 * k + 1], 1u));
+#ifdef FUSED_TIMING
+        if (g_fused_timing != nullptr) g_fused_timing[frame * 6 + 3] = fused_now();
+#endif
       }
       __syncwarp();
     }
@@ -425,11 +469,21 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
                                        (uint32_t)__double2hiint(acc), tag));
         }
       }
+#ifdef FUSED_TIMING
+      if (lane == 0 && g_fused_timing != nullptr) {
+        const unsigned long long now = fused_now();
+        atomicMin(g_fused_timing + frame * 6 + 0, now);
+        atomicMax(g_fused_timing + frame * 6 + 1, now);
+      }
+#endif
       __syncwarp();  // (the scratch is the output staging of the next GRAD item)
     }
 
     if (grad_valid) {
       // ---- GRAD ----------------------------------------------------------------------------------
+#ifdef FUSED_TIMING
+      if (lane == 0 && g_fused_timing != nullptr) atomicMin(g_fused_timing + grad_frame * 6 + 4, fused_now());
+#endif
       for (;;) {
         bool valid = true;
 #pragma unroll
@@ -439,6 +493,9 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 #pragma unroll
         for (int k = 0; k < FREC; ++k) pre[k] = ld_relaxed_gpu_v4(frames + grad_frame * FREC + k);
       }
+#ifdef FUSED_TIMING
+      if (lane == 0 && g_fused_timing != nullptr) atomicMax(g_fused_timing + grad_frame * 6 + 5, fused_now());
+#endif
       typename Policy::Frame fr;
       {
         uint32_t* words = reinterpret_cast<uint32_t*>(&fr);

@@ -306,3 +306,32 @@ def test_path_many_references_one_atom_set(metric, n_group, first, frames, miles
     outside = torch.ones(n, dtype=torch.bool)
     outside[atoms] = False
     assert not grad[:, outside].any()
+
+
+@pytest.mark.parametrize("frames", [4, 80])
+def test_rmsd_of_nearly_identical_frames(frames):
+    """RMSD close to zero on the streaming paths (4 frames: two-pass kernels, 80: fused kernel).  The
+    covariance is accumulated against the reference in double: a float copy is no longer centred, and
+    sum x (x) y^ then carries c (x) sum y^ -- 1e-9 in the mean square deviation, which is 100 % of an
+    RMSD of 3e-5 nm."""
+    rng = np.random.default_rng(38)
+    n = 4096
+    reference = rng.uniform(0.0, 2.5, size=(n, 3))
+    scales = np.logspace(-6, -2, frames)[:, None, None]
+    x = reference[None] + scales * rng.normal(size=(frames, n, 3))
+    x[0] = reference
+    system = unit_system(n)
+    rmsd = cvpack.RMSD(reference, range(n), n)
+    rmsd.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x)
+    stored = ctx.getPositions().double().cpu().numpy()
+    ref_value, ref_grad = c_oracle.rmsd_batch(stored, np.arange(n), reference)
+    value, grad = rmsd.getValueAndGradient(ctx)
+    v = value._value.double().cpu().numpy()
+    # 1e-5 relative, with an absolute floor of 1e-7 nm: the RMSD of the reference frame itself is
+    # rounding noise of (Gx + Gy - 2 lambda) ~ 1e-13 in both implementations (3e-8 vs 7e-8 nm)
+    assert np.all(np.abs(v - ref_value) <= 1e-5 * ref_value + 1e-7), np.abs(v - ref_value).max()
+    g = grad.double().cpu().numpy()
+    big = ref_value > 1e-4  # the gradient direction of a vanishing RMSD is ill-conditioned in FP32
+    err = np.abs(g[big] - ref_grad[big]).max(axis=(1, 2)) / np.abs(ref_grad[big]).max(axis=(1, 2))
+    assert err.max() <= 2e-3
