@@ -14,7 +14,10 @@ import typing as t
 import numpy as np
 
 _LIB_NAME = "libcvpack_b200.so"
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+# (CVPACK_B200_LIB: another build of the same library, e.g. a tuning variant -- never a fallback)
+_LIB_PATH = os.environ.get("CVPACK_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), _LIB_NAME
+)
 
 CVP_F32, CVP_F64 = 0, 1
 CVP_BOX_NONE, CVP_BOX_SHARED, CVP_BOX_PER_FRAME = 0, 1, 2

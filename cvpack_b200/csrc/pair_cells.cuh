@@ -35,7 +35,10 @@ constexpr int CELL_TILE = 32;          // i atoms per warp
 constexpr int CELL_SORT_THREADS = 512;
 constexpr int CELL_MAX_AXIS = 16;      // cells per axis (<= 4096 cells)
 constexpr int CELL_MAX_CELLS = CELL_MAX_AXIS * CELL_MAX_AXIS * CELL_MAX_AXIS;
-constexpr int CELL_SWEEP_THREADS = 512;
+#ifndef CELL_SWEEP_THREADS_VALUE
+#define CELL_SWEEP_THREADS_VALUE 512
+#endif
+constexpr int CELL_SWEEP_THREADS = CELL_SWEEP_THREADS_VALUE;
 constexpr int CELL_SMEM_BUDGET = 64 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
 constexpr int CELL_SMEM_BUDGET_SYM = 72 * 1024;  // ... with the j gradient accumulators
 constexpr int TAG_DUMMY = -1;

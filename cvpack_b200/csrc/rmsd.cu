@@ -625,8 +625,8 @@ struct RmsdCV : cvp_cv {
   int use_fused = 1;    // option "fused": one-read persistent kernel for the streaming fast path
   // measured on the 100k-atom batch: the per-frame solve (record gather + QCP) takes a few rounds,
   // and waiting for it costs more than the L2 misses of a long lag
-  int fused_lag = 8;    // option "fused_lag": rounds between the sums and the gradient of a frame
-  int fused_slice = 1024;  // option "fused_slice": atoms per sub-slice (0 = chosen by the planner)
+  int fused_lag = 2;    // option "fused_lag": rounds between the sums and the gradient of a frame
+  int fused_slice = 640;  // option "fused_slice": atoms per sub-slice (0 = chosen by the planner)
   int fused_slots = 0;  // option "fused_slots": auxiliary-data slots per CTA (0 = planner)
   int fused_hints = 3;  // option "fused_hints": L2 eviction hints (see FusedGeom::l2_hints)
   int fast_first = 0, fast_nslice = 0;

@@ -41,12 +41,21 @@
 
 namespace cvp {
 
-constexpr int FUSED_STAGES = 2;         // ring stages per warp (refilled right after the LDS)
+#ifndef FUSED_STAGES_VALUE
+#define FUSED_STAGES_VALUE 2
+#endif
+#ifndef FUSED_OUT_BUFS_VALUE
+#define FUSED_OUT_BUFS_VALUE 1
+#endif
+constexpr int FUSED_STAGES = FUSED_STAGES_VALUE;  // ring stages per warp (refilled right after the LDS)
+constexpr int FUSED_OUT_BUFS = FUSED_OUT_BUFS_VALUE;  // output staging buffers per warp (1 or 2)
 constexpr int FUSED_CHUNK_ATOMS = 256;  // 2 x 4 atoms (2 x 3 float4) per lane
 constexpr int FUSED_CHUNK_BYTES = FUSED_CHUNK_ATOMS * 12;
 constexpr int FUSED_MAX_WARPS = 15;  // streaming warps; with the solver warp 16 warps = 128 registers
 constexpr int FUSED_SMEM_LIMIT = 227 * 1024;
 constexpr int FUSED_SCRATCH_ROW = 33;  // doubles per row of the warp reduction scratch (padded)
+constexpr int FUSED_GATHER_BYTES = 24 * 1024;  // solver's staging of one segment of partial records
+constexpr int FUSED_GATHER_UNROLL = 4;         // probes in flight per lane: <= 128 slices per segment
 
 __device__ __forceinline__ void fused_unpack4(const float4& a0, const float4& a1, const float4& a2,
                                               float (&x)[4], float (&y)[4], float (&z)[4]) {
@@ -198,6 +207,7 @@ struct FusedGeom {
   int ring_rounds;     // rounds of partial sums kept (ring) -- T when there is no gradient
   int l2_hints;        // bit 0: evict_last for the first read, bit 1: evict_first for second read
                        // and stores
+  int gather_slices;   // sub-slices per segment of the solver's gather (<= 32 * FUSED_GATHER_UNROLL)
 };
 
 // Policy:
@@ -219,8 +229,9 @@ template <typename Policy>
 struct FusedLayout {
   static constexpr int NS = Policy::NS;
   static constexpr int SCRATCH_BYTES = (NS * FUSED_SCRATCH_ROW * 8 + 15) / 16 * 16;
-  static constexpr int OUT_BYTES =
-      2 * FUSED_CHUNK_BYTES > SCRATCH_BYTES ? 2 * FUSED_CHUNK_BYTES : SCRATCH_BYTES;
+  static constexpr int OUT_BYTES = FUSED_OUT_BUFS * FUSED_CHUNK_BYTES > SCRATCH_BYTES
+                                       ? FUSED_OUT_BUFS * FUSED_CHUNK_BYTES
+                                       : SCRATCH_BYTES;
   static constexpr int RING_BYTES = FUSED_STAGES * FUSED_CHUNK_BYTES;
   static constexpr int WARP_BYTES = (RING_BYTES + OUT_BYTES + FUSED_STAGES * 8 + 127) / 128 * 128;
   static int slot_bytes(int sub) {
@@ -240,13 +251,14 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
   constexpr int AUX = Policy::AUX;
   constexpr int AUXD = Policy::AUXD;
   constexpr int CH = FUSED_CHUNK_BYTES;
-  static_assert(FUSED_STAGES == 2, "the ring logic below assumes two stages");
+  static_assert(FUSED_STAGES >= 2 && FUSED_OUT_BUFS >= 1 && FUSED_OUT_BUFS <= 2, "ring geometry");
   static_assert(sizeof(typename Policy::Frame) == 64, "Frame must be 64 bytes");
   // frame constants travel as FREC records {c[2k], tag, c[2k+1], tag}
   constexpr int FREC = (Policy::FRAME_FLOATS + 1) / 2;
   static_assert(NS <= 16, "at most 16 sums");
   extern __shared__ __align__(128) unsigned char fused_smem[];
   __shared__ uint64_t s_aux_bar[FUSED_MAX_WARPS];
+  __shared__ uint64_t s_gather_bar;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // (warp-uniform for the compiler)
   const int lane = threadIdx.x & 31;
@@ -267,9 +279,12 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
   unsigned char* s_out = warp_base + Layout::RING_BYTES;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out + Layout::OUT_BYTES);
   if (warp < wpc && lane == 0) {
-    mbar_init(s_bar, 1);
-    mbar_init(s_bar + 1, 1);
+    for (int k = 0; k < FUSED_STAGES; ++k) mbar_init(s_bar + k, 1);
     if (warp < geom.slots) mbar_init(s_aux_bar + warp, 1);
+    mbar_fence_init();
+  }
+  if (warp == wpc && lane == 0) {
+    mbar_init(&s_gather_bar, 1);
     mbar_fence_init();
   }
   __syncthreads();  // the only block-wide barrier: the aux barriers are shared between warps
@@ -285,6 +300,9 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
     // with fewer CTAs than classes a solver takes several classes, round by round
     const int class_stride = gridDim.x < (unsigned)RR ? (int)gridDim.x : RR;
     if (gridDim.x >= (unsigned)RR && solver_phase >= M) return;
+    uint4* s_gather = reinterpret_cast<uint4*>(
+        fused_smem + (size_t)geom.slots * slot_bytes + (size_t)wpc * Layout::WARP_BYTES);
+    uint32_t gather_parity = 0;
     for (int round = gridDim.x >= (unsigned)RR ? solver_phase : 0; round < T;
          round += gridDim.x >= (unsigned)RR ? M : 1)
     for (int cls = solver_class; cls < RR; cls += class_stride) {
@@ -295,23 +313,59 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
       double sums[NS];
 #pragma unroll
       for (int k = 0; k < NS; ++k) sums[k] = 0.0;
-      const uint4* in = partials + slot * SS * NS;
-      for (int q = lane; q < SS; q += 32) {
-        const uint4* rec = in + (size_t)q * NS;
-        // one batch of NS independent L2 loads per attempt (re-reading a record at a time costs a
-        // round trip per late record, and volatile loads end up interleaved with their own checks)
-        uint4 v[NS];
+      // Gather in segments of GS sub-slices, two L2 round trips per segment once the records are
+      // there: (1) probe the last record of every sub-slice of the segment (<= FUSED_GATHER_UNROLL
+      // independent 16-byte loads per lane) until all carry the round's tag; (2) one bulk copy of
+      // the segment's records to shared memory, every tag checked there.  (Reading the records
+      // into registers, a batch of NS per lane and 32 sub-slices at a time, was SS / 32 dependent
+      // round trips: 12 us of the 10 us a round lasts.)
+      const int GS = geom.gather_slices;
+      for (int seg0 = 0; seg0 < SS; seg0 += GS) {
+        const int nseg = min(GS, SS - seg0);
+        const uint4* in = partials + (slot * SS + seg0) * NS;
         for (;;) {
+          uint4 probe[FUSED_GATHER_UNROLL];
 #pragma unroll
-          for (int k = 0; k < NS; ++k) v[k] = ld_cg_v4(rec + k);
-          bool valid = true;
+          for (int i = 0; i < FUSED_GATHER_UNROLL; ++i) {
+            const int q = lane + 32 * i;
+            probe[i] = q < nseg ? ld_cg_v4(in + (size_t)q * NS + (NS - 1)) : make_uint4(0u, tag, 0u, tag);
+          }
+          bool there = true;
 #pragma unroll
-          for (int k = 0; k < NS; ++k) valid = valid && v[k].y == tag && v[k].w == tag;
-          if (valid) break;
+          for (int i = 0; i < FUSED_GATHER_UNROLL; ++i)
+            there = there && probe[i].y == tag && probe[i].w == tag;
+          if (__all_sync(0xffffffffu, there)) break;
           __nanosleep(100);
         }
+        const uint32_t bytes = (uint32_t)nseg * NS * 16u;
+        for (;;) {
+          if (lane == 0) {
+            mbar_expect_tx(&s_gather_bar, bytes);
+            tma_load_1d_hint(s_gather, in, bytes, &s_gather_bar, pol_stream);
+          }
+          mbar_wait(&s_gather_bar, gather_parity);
+          gather_parity ^= 1u;
+          double seg_sums[NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) sums[k] += __hiloint2double((int)v[k].z, (int)v[k].x);
+          for (int k = 0; k < NS; ++k) seg_sums[k] = sums[k];
+          bool valid = true;
+          for (int q = lane; q < nseg; q += 32) {
+            const uint4* rec = s_gather + q * NS;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+              const uint4 v = rec[k];
+              valid = valid && v.y == tag && v.w == tag;
+              seg_sums[k] += __hiloint2double((int)v.z, (int)v.x);
+            }
+          }
+          // (all lanes have read the staging before lane 0 may refill it)
+          if (__all_sync(0xffffffffu, valid)) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) sums[k] = seg_sums[k];
+            break;
+          }
+          __nanosleep(100);
+        }
       }
 #pragma unroll
       for (int k = 0; k < NS; ++k) sums[k] = warp_sum(sums[k]);
@@ -381,7 +435,7 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
       tma_load_1d_hint(s_ring + p_stage * CH, p_ptr, bytes, s_bar + p_stage,
                        p_half == 0 && has_grad ? pol_keep : pol_stream);
     }
-    p_stage ^= 1;
+    p_stage = p_stage + 1 == FUSED_STAGES ? 0 : p_stage + 1;
     p_ptr += CH / 4;
     if (--p_left == 0) {
       for (;;) {
@@ -397,11 +451,11 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
       p_ptr = slice_base + ((int64_t)(p_half == 0 ? p_t : p_t - L) * RR + r) * frame_stride;
     }
   };
-  produce();
-  produce();
+  for (int k = 0; k < FUSED_STAGES; ++k) produce();
   if (AUX + AUXD > 0) mbar_wait(s_aux_bar + my_slot, 0);
 
-  uint32_t cons_q = 0;     // chunks consumed: stage = q & 1, parity = (q >> 1) & 1
+  int c_stage = 0;         // ring stage of the next chunk to consume ...
+  uint32_t c_parity = 0;   // ... and the parity its barrier completes with
   int out_buf = 0;
   const float4* lane_ring = reinterpret_cast<const float4*>(s_ring) + 3 * lane;
   const float* lane_aux = s_aux + lane * 4 * AUX;
@@ -414,8 +468,10 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
     const bool grad_valid = job_valid(t, 1);
     const int64_t grad_frame = (int64_t)(t - L) * RR + r;
     if (grad_valid) {
+      // (with a lag of one round the frame's sums have only just been written: fetch when needed)
 #pragma unroll
-      for (int k = 0; k < FREC; ++k) pre[k] = ld_relaxed_gpu_v4(frames + grad_frame * FREC + k);
+      for (int k = 0; k < FREC; ++k)
+        pre[k] = L > 1 ? ld_relaxed_gpu_v4(frames + grad_frame * FREC + k) : make_uint4(0u, 0u, 0u, 0u);
     }
 
     if (job_valid(t, 0)) {
@@ -428,9 +484,12 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
       const float* aux = lane_aux;
       const double2* auxd = lane_auxd;
       for (int c = 0; c < nch; ++c, left -= 64, aux += 64 * 4 * AUX, auxd += 64 * AUXD * 2) {
-        const int stage = cons_q & 1;
-        mbar_wait(s_bar + stage, (cons_q >> 1) & 1);
-        ++cons_q;
+        const int stage = c_stage;
+        mbar_wait(s_bar + stage, c_parity);
+        if (++c_stage == FUSED_STAGES) {
+          c_stage = 0;
+          c_parity ^= 1u;
+        }
         const float4* px = lane_ring + stage * (CH / 16);
         if (lane < left) {
           float x[4], y[4], z[4];
@@ -484,12 +543,12 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
 #ifdef FUSED_TIMING
       if (lane == 0 && g_fused_timing != nullptr) atomicMin(g_fused_timing + grad_frame * 6 + 4, fused_now());
 #endif
-      for (;;) {
+      for (bool first = true;; first = false) {
         bool valid = true;
 #pragma unroll
         for (int k = 0; k < FREC; ++k) valid = valid && pre[k].y == 1u && pre[k].w == 1u;
         if (__all_sync(0xffffffffu, valid)) break;
-        __nanosleep(200);
+        if (!first) __nanosleep(100);  // (the first re-read follows the prefetch without a pause)
 #pragma unroll
         for (int k = 0; k < FREC; ++k) pre[k] = ld_relaxed_gpu_v4(frames + grad_frame * FREC + k);
       }
@@ -509,12 +568,15 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
       int left = ng;
       const float* aux = lane_aux;
       for (int c = 0; c < nch; ++c, left -= 64, aux += 64 * 4 * AUX, gdst += CH / 4) {
-        const int stage = cons_q & 1;
-        mbar_wait(s_bar + stage, (cons_q >> 1) & 1);
-        ++cons_q;
+        const int stage = c_stage;
+        mbar_wait(s_bar + stage, c_parity);
+        if (++c_stage == FUSED_STAGES) {
+          c_stage = 0;
+          c_parity ^= 1u;
+        }
         const float4* px = lane_ring + stage * (CH / 16);
-        // the staging buffer written two chunks ago must have been read by its bulk store
-        if (lane == 0) tma_wait_group_read<1>();
+        // the staging buffer about to be written must have been read by its bulk store
+        if (lane == 0) tma_wait_group_read<FUSED_OUT_BUFS - 1>();
         __syncwarp();
         float4* po = reinterpret_cast<float4*>(s_out + out_buf * CH) + 3 * lane;
         if (lane < left) {
@@ -544,7 +606,7 @@ __global__ void __launch_bounds__((FUSED_MAX_WARPS + 1) * 32, 1)
             tma_store_1d(gdst, s_out + out_buf * CH, bytes, pol_stream);
           tma_commit_group();
         }
-        out_buf ^= 1;
+        if (FUSED_OUT_BUFS == 2) out_buf ^= 1;
       }
     }
   }
@@ -562,6 +624,11 @@ struct FusedLaunch {
     return ss_max * Policy::NS * sizeof(uint4) + 2 * sizeof(typename Policy::Frame) + 16;
   }
   static size_t workspace_fixed() { return 8 * 256 + sizeof(typename Policy::Frame); }
+  // segment of the solver's gather: as many sub-slices as fit the staging and the probe batch
+  static int gather_slices(int SS) {
+    return std::min(SS, std::min(32 * FUSED_GATHER_UNROLL, FUSED_GATHER_BYTES / (Policy::NS * 16)));
+  }
+  static int gather_bytes(int SS) { return (gather_slices(SS) * Policy::NS * 16 + 127) / 128 * 128; }
 
   // Chooses the sub-slice size and how many warps share one auxiliary-data slot: fills the
   // resident warps with as little rounding loss as possible; larger sub-slices (fewer per-item
@@ -580,7 +647,8 @@ struct FusedLaunch {
       for (int slots = 1; slots <= FUSED_MAX_WARPS; ++slots) {
         if (slots_option > 0 && slots != slots_option) continue;
         if (Policy::AUX == 0 && slots_option <= 0 && slots != FUSED_MAX_WARPS) continue;
-        const int budget = FUSED_SMEM_LIMIT - 1024 - slots * Layout::slot_bytes(sub);
+        const int budget =
+            FUSED_SMEM_LIMIT - 1024 - gather_bytes((int)SS) - slots * Layout::slot_bytes(sub);
         if (budget <= 0) continue;
         int wpc = std::min(FUSED_MAX_WARPS, budget / Layout::WARP_BYTES);
         wpc = wpc / slots * slots;
@@ -622,6 +690,7 @@ struct FusedLaunch {
     g.L = std::max(1, std::min(lag_rounds, g.T));
     g.ring_rounds = has_grad ? std::min(g.T, g.L + 2) : g.T;  // (== T: records indexed by frame)
     g.l2_hints = l2_hints;
+    g.gather_slices = gather_slices(g.SS);
     *geom = g;
     return true;
   }
@@ -642,7 +711,7 @@ struct FusedLaunch {
     CVP_CUDA_CHECK(cudaMemsetAsync(frames, 0, B * FREC * sizeof(uint4), stream));
     CVP_CUDA_CHECK(cudaMemsetAsync(partials, 0, records * sizeof(uint4), stream));  // tag 0 = empty
     const size_t smem = (size_t)geom.slots * Layout::slot_bytes(geom.sub) +
-                        (size_t)geom.warps_per_cta * Layout::WARP_BYTES;
+                        (size_t)geom.warps_per_cta * Layout::WARP_BYTES + gather_bytes(geom.SS);
     static bool configured = false;
     if (!configured) {
       CVP_CUDA_CHECK(cudaFuncSetAttribute(stream_fused_kernel<Policy>,
