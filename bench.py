@@ -298,6 +298,10 @@ def run_ours(args, spec: dict) -> None:
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed to stdout
+        # at NCCL_DEBUG=VERSION and above) goes to a file unless the caller asked for a debug file
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(os.environ.get("TMPDIR", "/tmp"), "nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")

@@ -7,7 +7,7 @@ effective mass); evaluation runs hand-written sm_100a CUDA kernels over a whole 
 (:class:`BatchContext`) instead of one ``openmm.Context`` call per frame.
 """
 
-from . import app, mm, mmunit, path, serialization, units  # noqa: F401
+from . import app, bias, mm, mmunit, path, serialization, trajectory, units  # noqa: F401
 from ._version import __version__  # noqa: F401
 from .angle import Angle  # noqa: F401
 from .attraction_strength import AttractionStrength  # noqa: F401
@@ -31,6 +31,7 @@ from .sheet_rmsd_content import SheetRMSDContent  # noqa: F401
 from .shortest_distance import ShortestDistance  # noqa: F401
 from .torsion import Torsion  # noqa: F401
 from .torsion_similarity import TorsionSimilarity  # noqa: F401
+from .trajectory import DCDFile, NumpyTrajectory, TrajectoryEvaluator  # noqa: F401
 
 __all__ = [
     "Angle",

@@ -1,0 +1,261 @@
+"""Trajectory ingestion and walker coupling (rank 4): host logic on the CPU,
+the streamed evaluation and the in-place bias forces on the GPU against the oracle."""
+
+import io
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+import cvpack_b200 as cvpack
+from cvpack_b200 import bias as cvbias
+from cvpack_b200.trajectory import DCDFile, NumpyTrajectory, TrajectoryEvaluator, open_trajectory
+from tests import helpers
+
+
+def _frames(rng, frames, atoms, scale=2.0):
+    return rng.uniform(-scale, scale, size=(frames, atoms, 3))
+
+
+# ---- host logic (no GPU) ---------------------------------------------------------------------------
+def test_dcd_round_trip_without_box(tmp_path):
+    rng = np.random.default_rng(7)
+    x = _frames(rng, 5, 13)
+    path = tmp_path / "a.dcd"
+    DCDFile.write(path, x, firstStep=100, interval=50)
+    dcd = DCDFile(path)
+    assert (len(dcd), dcd.numAtoms, dcd.hasBox, dcd.firstStep, dcd.interval) == (5, 13, False, 100, 50)
+    pos, box = dcd.read(0, 5)
+    assert box is None and pos.dtype == np.float32 and pos.shape == (5, 13, 3)
+    # stored as float32 Angstrom: exactly the correctly rounded quotient of the stored value
+    stored = (x * 10.0).astype(np.float32)
+    assert np.array_equal(pos, stored / np.float32(10.0))
+    assert np.allclose(pos, x, rtol=0, atol=2e-6)
+    part, _ = dcd.read(2, 2)
+    assert np.array_equal(part, pos[2:4])
+    with pytest.raises(IndexError):
+        dcd.read(4, 2)
+
+
+def test_dcd_header_layout_matches_the_format(tmp_path):
+    """Byte-level check of the writer against the CHARMM layout OpenMM's DCDReporter emits."""
+    path = tmp_path / "b.dcd"
+    DCDFile.write(path, np.zeros((2, 3, 3)), boxVectors=[2.0, 3.0, 4.0], timeStep=0.5)
+    raw = path.read_bytes()
+    assert struct.unpack("<i", raw[:4])[0] == 84 and raw[4:8] == b"CORD"
+    icntrl = struct.unpack("<20i", raw[8:88])
+    assert icntrl[0] == 2 and icntrl[10] == 1 and icntrl[19] == 24
+    assert struct.unpack("<f", raw[8 + 36:8 + 40])[0] == 0.5
+    assert struct.unpack("<i", raw[88:92])[0] == 84
+    title_len = struct.unpack("<i", raw[92:96])[0]
+    assert title_len == 84 and struct.unpack("<i", raw[96:100])[0] == 1
+    offset = 96 + title_len + 4
+    assert struct.unpack("<3i", raw[offset:offset + 12]) == (4, 3, 4)
+    offset += 12
+    frame_bytes = (4 + 48 + 4) + 3 * (4 + 12 + 4)
+    assert len(raw) == offset + 2 * frame_bytes
+    assert struct.unpack("<i", raw[offset:offset + 4])[0] == 48
+    cell = struct.unpack("<6d", raw[offset + 4:offset + 52])
+    assert cell == (20.0, 90.0, 30.0, 90.0, 90.0, 40.0)  # A gamma B beta alpha C (Angstrom, degrees)
+
+
+@pytest.mark.parametrize("cosines", [False, True])
+def test_dcd_triclinic_box_round_trip(tmp_path, cosines):
+    rng = np.random.default_rng(8)
+    x = _frames(rng, 3, 4)
+    boxes = np.zeros((3, 3, 3))
+    for b in range(3):
+        boxes[b] = [[3.0 + b, 0, 0], [0.5, 2.5, 0], [-0.4, 0.3, 2.0 + 0.1 * b]]
+    path = tmp_path / "c.dcd"
+    DCDFile.write(path, x, boxVectors=boxes)
+    if cosines:  # CHARMM >= 25 stores the cosines of the angles instead of degrees
+        dcd = DCDFile(path)
+        raw = bytearray(path.read_bytes())
+        frame = dcd._dtype.itemsize  # pylint: disable=protected-access
+        for b in range(3):
+            at = dcd._offset + b * frame + 4  # pylint: disable=protected-access
+            cell = list(struct.unpack("<6d", raw[at:at + 48]))
+            for k in (1, 3, 4):
+                cell[k] = np.cos(np.deg2rad(cell[k]))
+            raw[at:at + 48] = struct.pack("<6d", *cell)
+        del dcd
+        path.write_bytes(bytes(raw))
+    _, got = DCDFile(path).read(0, 3)
+    assert np.allclose(got, boxes, atol=1e-12)
+    assert np.all(got[:, 0, 1:] == 0) and np.all(got[:, 1, 2] == 0)  # reduced form, exact zeros
+    rect = tmp_path / "d.dcd"
+    DCDFile.write(rect, x, boxVectors=np.diag([2.0, 3.0, 4.0]))
+    _, got = DCDFile(rect).read(1, 1)
+    assert np.array_equal(got[0], np.diag([2.0, 3.0, 4.0]))
+
+
+def test_dcd_rejects_foreign_files(tmp_path):
+    path = tmp_path / "x.dcd"
+    path.write_bytes(b"\0" * 200)
+    with pytest.raises(ValueError, match="not a little-endian CORD DCD"):
+        DCDFile(path)
+    big = tmp_path / "y.dcd"  # big-endian marker
+    big.write_bytes(struct.pack(">i", 84) + b"CORD" + b"\0" * 200)
+    with pytest.raises(ValueError):
+        DCDFile(big)
+
+
+def test_numpy_trajectory_and_npy_memmap(tmp_path):
+    rng = np.random.default_rng(9)
+    x = _frames(rng, 6, 5).astype(np.float32)
+    np.save(tmp_path / "t.npy", x)
+    traj = open_trajectory(str(tmp_path / "t.npy"))
+    assert isinstance(traj, NumpyTrajectory) and len(traj) == 6 and not traj.hasBox
+    out = np.empty((2, 5, 3), dtype=np.float32)
+    got, box = traj.read(3, 2, out)
+    assert got is out and box is None and np.array_equal(out, x[3:5])
+    boxed = NumpyTrajectory(x, boxVectors=[2.0, 2.0, 2.0])
+    _, box = boxed.read(0, 6)
+    assert box.shape == (6, 3, 3) and np.array_equal(box[5], np.diag([2.0, 2.0, 2.0]))
+    with pytest.raises(ValueError):
+        NumpyTrajectory(np.zeros((3, 4)))
+
+
+def test_evaluator_headers_follow_the_reference_writer():
+    """`name (unit)` / `emass[name] (mass unit)` (reference reporting/cv_writer.py:92-100)."""
+    system = cvpack.System()
+    for _ in range(20):
+        system.addParticle(1.0)
+    phi = cvpack.Torsion(6, 8, 14, 16, name="phi")
+    psi = cvpack.Torsion(8, 14, 16, 18, name="psi")
+    phi.addToSystem(system)
+    psi.addToSystem(system)
+    evaluator = TrajectoryEvaluator(system, [phi, psi], value=True, emass=True)
+    assert evaluator.getHeaders() == [
+        "phi (rad)", "emass[phi] (nm**2 Da/(rad**2))", "psi (rad)", "emass[psi] (nm**2 Da/(rad**2))",
+    ]
+    with pytest.raises(ValueError, match="At least one of value or effective_mass must be True"):
+        TrajectoryEvaluator(system, [phi], value=False, emass=False)
+    stray = cvpack.Distance(0, 1)
+    with pytest.raises(RuntimeError, match="This force is not present in the given context."):
+        TrajectoryEvaluator(system, [stray])
+    out = io.StringIO()
+    table = {"phi (rad)": np.array([1.5, -2.0]), "emass[phi] (nm**2 Da/(rad**2))": np.array([0.05, np.inf])}
+    evaluator.writeCSV(out, table, firstStep=100, interval=100)
+    assert out.getvalue().splitlines() == [
+        '#"Step","phi (rad)","emass[phi] (nm**2 Da/(rad**2))"', "100,1.5,0.05", "200,-2.0,inf",
+    ]
+
+
+def test_bias_functions_against_finite_differences():
+    s = torch.linspace(-3.0, 3.0, 41, dtype=torch.float64)
+    h = 1e-6
+    harmonic = cvbias.HarmonicBias(12.5, 0.4, period=2 * np.pi)
+    hills = cvbias.GaussianHillsBias(0.3, period=2 * np.pi)
+    assert hills.getNumHills() == 0 and float(hills.energy(s).abs().max()) == 0.0
+    hills.addHills(torch.tensor([-2.9, 0.1, 3.0]), 1.2)
+    hills.addHills(torch.tensor([0.5]), torch.tensor([0.7]))
+    assert hills.getNumHills() == 4
+    for bias in (harmonic, hills):
+        fd = (bias.energy(s + h) - bias.energy(s - h)) / (2 * h)
+        assert torch.allclose(bias.derivative(s), fd, atol=1e-6)
+    # periodic image: a hill at -2.9 is felt just below +pi
+    assert float(hills.energy(torch.tensor([3.3], dtype=torch.float64))) > 1.0
+
+
+# ---- GPU -------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_box", [False, True])
+def test_streamed_dcd_matches_whole_batch_and_oracle(tmp_path, with_box):
+    rng = np.random.default_rng(11)
+    frames, n = 37, 60  # ragged last chunk: 37 = 3 * 10 + 7
+    box = np.array([3.0, 3.2, 3.4])
+    x = rng.uniform(0.0, 3.0, size=(frames, n, 3))
+    system = helpers.make_system(n, rng, box=np.diag(box) if with_box else None)
+    rg = cvpack.RadiusOfGyration(range(10, 40), name="rg")
+    nonbonded = helpers.make_nonbonded(n, rng, periodic=with_box, cutoff=1.0)
+    contacts = cvpack.NumberOfContacts(range(0, 30), range(30, 60), nonbonded, name="nc")
+    torsion = cvpack.Torsion(1, 5, 9, 13, pbc=with_box, name="phi")
+    for cv in (rg, contacts, torsion):
+        cv.addToSystem(system)
+    path = tmp_path / "traj.dcd"
+    boxes = None
+    if with_box:  # a different (rectangular) box per frame
+        boxes = np.stack([np.diag(box * (1.0 + 0.01 * b)) for b in range(frames)])
+    DCDFile.write(path, x, boxVectors=boxes)
+    stored, stored_box = DCDFile(path).read(0, frames)
+
+    evaluator = TrajectoryEvaluator(system, [rg, contacts, torsion], value=True, emass=True, chunkFrames=10)
+    table = evaluator.evaluate(str(path))
+    assert list(table) == evaluator.getHeaders()
+
+    ctx = cvpack.BatchContext(system, stored, None if stored_box is None else stored_box)
+    for cv in (rg, contacts, torsion):
+        # (value and gradient in one pass, as the evaluator does when it reports effective masses)
+        whole = cv.getValueAndGradient(ctx)[0]._value.double().cpu().numpy()
+        emass = cv.getEffectiveMass(ctx)._value.double().cpu().numpy()
+        name = cv.getName()
+        assert np.array_equal(table[f"{name} ({cv.getUnit().get_symbol()})"], whole)  # bitwise
+        assert np.array_equal(table[f"emass[{name}] ({cv.getMassUnit().get_symbol()})"], emass)
+        for b in (0, 9, 10, 36):
+            ref, _ = helpers.oracle_evaluate(
+                cv, system, stored[b].astype(np.float64), None if stored_box is None else stored_box[b]
+            )
+            assert whole[b] == pytest.approx(ref, rel=1e-5, abs=1e-6)
+    sub = evaluator.evaluate(str(path), start=5, stop=23)
+    assert np.array_equal(sub["rg (nm)"], table["rg (nm)"][5:23])
+    assert len(evaluator.evaluate(str(path), start=30, stop=30)["rg (nm)"]) == 0
+
+
+@pytest.mark.gpu
+def test_streamed_array_value_only_and_atom_mismatch():
+    rng = np.random.default_rng(12)
+    frames, n = 25, 33
+    x = rng.normal(size=(frames, n, 3)).astype(np.float32)
+    system = helpers.make_system(n, rng)
+    rmsd = cvpack.RMSD(x[0].astype(np.float64), range(n), n, name="rmsd")
+    rmsd.addToSystem(system)
+    table = TrajectoryEvaluator(system, [rmsd], chunkFrames=4).evaluate(x)
+    ctx = cvpack.BatchContext(system, x)
+    assert np.array_equal(table["rmsd (nm)"], rmsd.getValue(ctx)._value.double().cpu().numpy())
+    assert table["rmsd (nm)"][0] == pytest.approx(0.0, abs=1e-6)
+    with pytest.raises(ValueError, match="atoms"):
+        TrajectoryEvaluator(system, [rmsd]).evaluate(np.zeros((2, n + 1, 3), dtype=np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_bias_forces_in_place(precision):
+    rng = np.random.default_rng(13)
+    walkers, n = 19, 48
+    x = rng.uniform(0.0, 2.0, size=(walkers, n, 3))
+    system = helpers.make_system(n, rng)
+    phi = cvpack.Torsion(0, 7, 11, 20, name="phi")
+    rg = cvpack.RadiusOfGyration(range(5, 40), name="rg")
+    phi.addToSystem(system)
+    rg.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, precision=precision)
+    hills = cvbias.GaussianHillsBias(0.4, period=2 * np.pi)
+    hills.addHills(torch.tensor([0.3, -1.0, 2.5]), 2.0)
+    spring = cvbias.HarmonicBias(50.0, 0.7)
+    dtype = torch.float32 if precision == "single" else torch.float64
+    base = torch.as_tensor(rng.normal(size=(walkers, n, 3)), dtype=dtype, device=ctx.getDevice())
+    forces = base.clone()
+    out, values, energy = cvbias.applyBias(ctx, [phi, rg], [hills, spring], forces)
+    assert out is forces and values.shape == (2, walkers)
+    tol = 1e-5 if precision == "single" else 1e-10
+    xs = ctx.getPositions().double().cpu().numpy()
+    expected = base.double().cpu().numpy().copy()
+    total = np.zeros(walkers)
+    for b in range(walkers):
+        for cv, bias in ((phi, hills), (rg, spring)):
+            s, g = helpers.oracle_evaluate(cv, system, xs[b], None)
+            s_t = torch.tensor([s], dtype=torch.float64)
+            expected[b] -= float(bias.derivative(s_t)) * g
+            total[b] += float(bias.energy(s_t))
+    scale = np.abs(expected).max()
+    assert np.abs(forces.double().cpu().numpy() - expected).max() <= 20 * tol * scale
+    assert np.allclose(energy.double().cpu().numpy(), total, rtol=50 * tol, atol=50 * tol)
+    # without a force buffer: allocated, and exactly the bias part
+    fresh, _, _ = cvbias.applyBias(ctx, [phi, rg], [hills, spring])
+    assert np.abs((fresh - (forces - base)).double().cpu().numpy()).max() <= 20 * tol * scale
+    with pytest.raises(ValueError):
+        cvbias.accumulateBiasForces(forces, forces[:, :10].contiguous(), torch.zeros(walkers))
+    with pytest.raises(ValueError):
+        cvbias.accumulateBiasForces(forces.cpu(), forces.cpu(), torch.zeros(walkers))
