@@ -571,6 +571,122 @@ __global__ void rmsd_gradient_kernel(const T* __restrict__ pos, int64_t num_atom
   }
 }
 
+// ---- many small groups over few atoms: one CTA per frame -------------------------------------------
+// HelixRMSDContent / SheetRMSDContent (base_rmsd_content.py:56-102): hundreds of overlapping
+// 30-atom blocks over the backbone of one chain, value = scale * sum_g S(rmsd_g / r0).  The generic
+// path runs four kernels and moves every block through global memory (partials, solutions,
+// factors); here the frame's active atoms are staged once in shared memory, every thread owns whole
+// blocks (13 FP64 sums, QCP solve, step function), the per-block constants stay in shared memory
+// and the gradient is gathered per atom from them (single writer, fixed order: deterministic).
+constexpr int BLOCKS_THREADS = 256;
+constexpr int BLOCKS_SMEM_BUDGET = 200 * 1024;  // (two CTAs per SM up to half of it)
+constexpr int BLOCKS_SOL = 13;                  // doubles per block: c[3], U^T[9], factor
+
+template <typename T>
+__global__ void __launch_bounds__(BLOCKS_THREADS, 2)
+    rmsd_blocks_kernel(const T* __restrict__ pos, int64_t num_atoms,
+                       const int32_t* __restrict__ active_atom, int num_active,
+                       const int32_t* __restrict__ entry_slot, const int32_t* __restrict__ entry_group,
+                       const int32_t* __restrict__ group_entry_offsets, const double* __restrict__ ref,
+                       int shared_ref_entries, const double* __restrict__ group_gy, int num_groups,
+                       const int32_t* __restrict__ atom_entry_offsets,
+                       const int32_t* __restrict__ atom_entries, CombineParams cp,
+                       T* __restrict__ value, T* __restrict__ grad, int accumulate) {
+  extern __shared__ __align__(16) unsigned char blocks_smem[];
+  double* s_sol = reinterpret_cast<double*>(blocks_smem);                 // [num_groups][13]
+  double* s_ref = s_sol + (size_t)num_groups * BLOCKS_SOL;                // [shared_ref_entries][3]
+  T* s_x = reinterpret_cast<T*>(s_ref + (size_t)shared_ref_entries * 3);  // [num_active][3]
+  __shared__ double s_red[BLOCKS_THREADS];
+  const int64_t b = blockIdx.x;
+  const T* frame = pos + b * num_atoms * 3;
+  for (int k = threadIdx.x; k < num_active; k += BLOCKS_THREADS) {
+    const T* p = frame + 3 * (int64_t)active_atom[k];
+    s_x[3 * k] = p[0];
+    s_x[3 * k + 1] = p[1];
+    s_x[3 * k + 2] = p[2];
+  }
+  for (int k = threadIdx.x; k < shared_ref_entries * 3; k += BLOCKS_THREADS) s_ref[k] = ref[k];
+  __syncthreads();
+
+  double local = 0.0;
+  for (int g = threadIdx.x; g < num_groups; g += BLOCKS_THREADS) {
+    const int begin = group_entry_offsets[g], end = group_entry_offsets[g + 1];
+    double v[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) v[k] = 0.0;
+    for (int e = begin; e < end; ++e) {
+      const int slot = entry_slot[e];
+      const double x = s_x[3 * slot], y = s_x[3 * slot + 1], z = s_x[3 * slot + 2];
+      const double* r = shared_ref_entries ? s_ref + 3 * (e - begin) : ref + 3 * (int64_t)e;
+      const double rx = r[0], ry = r[1], rz = r[2];
+      v[0] += x;
+      v[1] += y;
+      v[2] += z;
+      v[3] += x * x + y * y + z * z;
+      v[4] += x * rx;
+      v[5] += x * ry;
+      v[6] += x * rz;
+      v[7] += y * rx;
+      v[8] += y * ry;
+      v[9] += y * rz;
+      v[10] += z * rx;
+      v[11] += z * ry;
+      v[12] += z * rz;
+    }
+    double rmsd, ut[9], c[3];
+    // QCP (Newton on the characteristic polynomial) in FP32 mode, cyclic Jacobi in FP64 mode, as
+    // the generic solve kernel: the 1e-10 bar of the FP64 mode leaves no room for the adjugate
+    rmsd_from_sums(v, group_gy[g], end - begin, sizeof(T) == 4, rmsd, ut, c);
+    double sv, ds;
+    step_function(cp.step, rmsd * cp.inv_r0, sv, ds);
+    local += sv;
+    double* sol = s_sol + (size_t)g * BLOCKS_SOL;
+    sol[0] = c[0];
+    sol[1] = c[1];
+    sol[2] = c[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sol[3 + k] = ut[k];
+    sol[12] = rmsd > 0.0 ? cp.scale * ds * cp.inv_r0 / ((end - begin) * rmsd) : 0.0;
+  }
+  s_red[threadIdx.x] = local;
+  __syncthreads();
+  for (int stride = BLOCKS_THREADS / 2; stride > 0; stride >>= 1) {
+    if (threadIdx.x < stride) s_red[threadIdx.x] += s_red[threadIdx.x + stride];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double result = cp.scale * s_red[0];
+    value[b] = accumulate ? value[b] + T(result) : T(result);
+  }
+  if (grad == nullptr) return;
+  for (int k = threadIdx.x; k < num_active; k += BLOCKS_THREADS) {
+    const double x = s_x[3 * k], y = s_x[3 * k + 1], z = s_x[3 * k + 2];
+    double gx = 0, gy = 0, gz = 0;
+    for (int m = atom_entry_offsets[k]; m < atom_entry_offsets[k + 1]; ++m) {
+      const int e = atom_entries[m];
+      const int g = entry_group[e];
+      const double* sol = s_sol + (size_t)g * BLOCKS_SOL;
+      const double f = sol[12];
+      if (f == 0.0) continue;
+      const double* r = shared_ref_entries ? s_ref + 3 * (e - group_entry_offsets[g]) : ref + 3 * (int64_t)e;
+      const double rx = r[0], ry = r[1], rz = r[2];
+      gx += f * (x - sol[0] - (sol[3] * rx + sol[4] * ry + sol[5] * rz));
+      gy += f * (y - sol[1] - (sol[6] * rx + sol[7] * ry + sol[8] * rz));
+      gz += f * (z - sol[2] - (sol[9] * rx + sol[10] * ry + sol[11] * rz));
+    }
+    T* out = grad + (b * num_atoms + active_atom[k]) * 3;
+    if (accumulate) {
+      out[0] += T(gx);
+      out[1] += T(gy);
+      out[2] += T(gz);
+    } else {
+      out[0] = T(gx);
+      out[1] = T(gy);
+      out[2] = T(gz);
+    }
+  }
+}
+
 // gradient of the streaming fast path: g = factor * (x - c - U^T y), 4 atoms per thread iteration
 __global__ void __launch_bounds__(RMSD_FAST_THREADS)
     rmsd_gradient_fast_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom,
@@ -648,6 +764,12 @@ struct RmsdCV : cvp_cv {
   std::vector<double> group_gy;
   std::vector<int32_t> atom_entry_offsets, atom_entries;
   bool dense = false;  // every atom of the system is active
+  // many small single-body groups summed through a step function (rmsd_blocks_kernel)
+  bool blocks = false;
+  int use_blocks = 1;          // option "blocks"
+  int blocks_shared_ref = 0;   // entries of the reference all groups share (0: per-group references)
+  std::vector<int32_t> entry_slot, group_entry_offsets;
+  DeviceBuffer d_entry_slot, d_group_entry_offsets;
   DeviceBuffer d_entry_atom, d_entry_group, d_entry_seg, d_ref, d_slices, d_group_seg_offsets,
       d_seg_slice_offsets, d_seg_size, d_group_size, d_group_gy, d_active, d_atom_entry_offsets,
       d_atom_entries;
@@ -656,7 +778,8 @@ struct RmsdCV : cvp_cv {
     for (DeviceBuffer* buf :
          {&d_entry_atom, &d_entry_group, &d_entry_seg, &d_ref, &d_slices, &d_group_seg_offsets,
           &d_seg_slice_offsets, &d_seg_size, &d_group_size, &d_group_gy, &d_active,
-          &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_ref_perm, &d_fast_seg_slice_offsets})
+          &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_ref_perm, &d_fast_seg_slice_offsets,
+          &d_entry_slot, &d_group_entry_offsets})
       buf->release();
   }
   int upload() override {
@@ -679,6 +802,8 @@ struct RmsdCV : cvp_cv {
     CVP_UP(d_ref_f32, ref_f32);
     CVP_UP(d_ref_perm, ref_perm);
     CVP_UP(d_fast_seg_slice_offsets, fast_seg_slice_offsets);
+    CVP_UP(d_entry_slot, entry_slot);
+    CVP_UP(d_group_entry_offsets, group_entry_offsets);
 #undef CVP_UP
     return CVP_OK;
   }
@@ -698,6 +823,10 @@ struct RmsdCV : cvp_cv {
     }
     if (key == "multi") {
       std::swap(use_multi, value);
+      return value;
+    }
+    if (key == "blocks") {
+      std::swap(use_blocks, value);
       return value;
     }
     if (key == "fused_lag") {
@@ -721,6 +850,11 @@ struct RmsdCV : cvp_cv {
   int64_t max_frames_per_run() const override {
     int64_t per_frame = std::max<int64_t>(nslice, (int64_t)active_atoms.size() / 64 + 1);
     return std::max<int64_t>(1, (int64_t(1) << 30) / per_frame);
+  }
+
+  size_t blocks_smem_bytes(size_t coordinate_bytes) const {
+    return ((size_t)num_groups * BLOCKS_SOL + (size_t)blocks_shared_ref * 3) * sizeof(double) +
+           active_atoms.size() * 3 * coordinate_bytes;
   }
 
   template <typename T>
@@ -755,6 +889,29 @@ struct RmsdCV : cvp_cv {
           accumulate, st);
       timer.end(st);
       return status;
+    }
+    if (blocks && use_blocks && blocks_smem_bytes(sizeof(T)) <= (size_t)BLOCKS_SMEM_BUDGET) {
+      const size_t smem = blocks_smem_bytes(sizeof(T));
+      static bool blocks_configured = false;
+      if (!blocks_configured) {
+        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_blocks_kernel<T>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            BLOCKS_SMEM_BUDGET));
+        blocks_configured = true;
+      }
+      if (grad != nullptr && !accumulate && !dense)
+        CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+      timer.begin("rmsd_blocks", st);
+      rmsd_blocks_kernel<T><<<(unsigned)B, BLOCKS_THREADS, smem, st>>>(
+          pos, N, static_cast<const int32_t*>(d_active.ptr), (int)active_atoms.size(),
+          static_cast<const int32_t*>(d_entry_slot.ptr), static_cast<const int32_t*>(d_entry_group.ptr),
+          static_cast<const int32_t*>(d_group_entry_offsets.ptr), static_cast<const double*>(d_ref.ptr),
+          blocks_shared_ref, static_cast<const double*>(d_group_gy.ptr), num_groups,
+          static_cast<const int32_t*>(d_atom_entry_offsets.ptr),
+          static_cast<const int32_t*>(d_atom_entries.ptr), cp, value, grad, accumulate ? 1 : 0);
+      timer.end(st);
+      CVP_LAUNCH_CHECK();
+      return CVP_OK;
     }
     const bool use_multi_path = multi && use_multi && std::is_same<T, float>::value;
     if (use_multi_path) {
@@ -877,6 +1034,13 @@ struct RmsdCV : cvp_cv {
 
 }  // namespace
 
+static bool B_blocks_fit(const RmsdCV& cv) {
+  // (FP32 coordinates, a shared reference of up to 64 entries; checked again per dtype at run time)
+  return ((size_t)cv.num_groups * BLOCKS_SOL + 64 * 3) * sizeof(double) +
+             cv.active_atoms.size() * 3 * sizeof(float) <=
+         (size_t)BLOCKS_SMEM_BUDGET;
+}
+
 int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
   CVP_REQUIRE(desc != nullptr && out != nullptr, "null argument");
   CVP_REQUIRE(desc->num_atoms > 0 && desc->num_groups > 0 && desc->group_offsets && desc->atoms &&
@@ -997,6 +1161,27 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
       cv->ref_perm = fused_permute_doubles(cv->ref.data(), (size_t)E);
       cv->fast_seg_slice_offsets = {0, cv->fast_nslice};
     }
+  }
+  // many small single-body groups summed through a step function (helix / sheet content): one CTA
+  // per frame when the frame's active atoms and the per-group constants fit in shared memory
+  if (desc->combine == CVP_COMBINE_STEP_SUM && cv->nseg == G && B_blocks_fit(*cv)) {
+    cv->blocks = true;
+    std::vector<int32_t> slot_of_atom(desc->num_atoms, -1);
+    for (size_t k = 0; k < cv->active_atoms.size(); ++k) slot_of_atom[cv->active_atoms[k]] = (int32_t)k;
+    cv->entry_slot.resize((size_t)E);
+    for (int64_t e = 0; e < E; ++e) cv->entry_slot[e] = slot_of_atom[cv->entry_atom[e]];
+    cv->group_entry_offsets.assign(1, 0);
+    for (int g = 0; g < G; ++g)
+      cv->group_entry_offsets.push_back(cv->group_entry_offsets.back() + cv->group_size[g]);
+    // one centred reference shared by all groups (bitwise), as the content CVs build them?
+    const int n0 = cv->group_size[0];
+    bool shared = n0 <= 64;
+    for (int g = 1; g < G && shared; ++g) {
+      shared = cv->group_size[g] == n0 &&
+               std::equal(cv->ref.begin(), cv->ref.begin() + 3 * (size_t)n0,
+                          cv->ref.begin() + 3 * (size_t)cv->group_entry_offsets[g]);
+    }
+    cv->blocks_shared_ref = shared ? n0 : 0;
   }
   // many references, one atom set: G >= 2 single-segment groups that all list atoms first,
   // first + 1, ..., first + n - 1 in this order

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 import cvpack_b200 as cvpack
-from cvpack_b200 import mmunit, serialization
+from cvpack_b200 import _native, mmunit, serialization
 from tests import helpers
 
 pytestmark = pytest.mark.gpu
@@ -471,3 +471,45 @@ def test_config0_solvated_dipeptide_single_frame(precision):
         helpers.check_against_oracle(cv, system, x[None], box, precision, vt, gt, context=ctx)
     emass = cvs[3].getEffectiveMass(ctx)
     assert np.isfinite(float(emass._value[0])) and float(emass._value[0]) > 0  # pylint: disable=protected-access
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_rmsd_content_one_cta_per_frame_equals_generic_kernels(precision):
+    """The shared-memory path of the content CVs (`rmsd_blocks_kernel`) against the four generic
+    kernels on the same frames: 200 residues (195 overlapping blocks), values and gradients; and
+    against the oracle on a few frames."""
+    rng = np.random.default_rng(61)
+    nres = 200
+    topology = helpers.make_peptide(nres, glycines=(7, 120))
+    n = topology.getNumAtoms()
+    system = helpers.make_system(n, rng)
+    base = helpers.ideal_helix_positions(nres, rng)
+    x = base[None] + rng.normal(scale=0.03, size=(70, n, 3))
+    x[5] = base  # an ideal frame: every block at rmsd ~ 0
+    cv = cvpack.HelixRMSDContent(list(topology.residues()), n)
+    cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, precision=precision)
+    native = ctx._native_cv(cv)  # pylint: disable=protected-access
+    launches = _native.launch_count()
+    value, grad = cv.getValueAndGradient(ctx)
+    assert _native.launch_count() - launches == 1  # one kernel for the whole batch
+    value, grad = value._value.clone(), grad.clone()
+    assert native.set_option("blocks", 0) == 1
+    value0, grad0 = cv.getValueAndGradient(ctx)
+    native.set_option("blocks", 1)
+    tol = 1e-5 if precision == "single" else 1e-10
+    assert torch.allclose(value, value0._value, rtol=tol, atol=0)
+    scale = float(grad0.abs().max())
+    # (the two paths add the 13 sums of a block in different orders; near rmsd = 0 the gradient
+    # (x - c - U^T y) / rmsd amplifies that, so the paths agree to 1e-8 in FP64 mode while each
+    # meets the 1e-10 bar against the oracle on the frames checked below)
+    assert float((grad - grad0).abs().max()) <= (tol if precision == "single" else 1e-8) * scale
+    # atoms outside the blocks (H of every residue) carry exactly zero gradient
+    outside = [a.index for a in topology.atoms() if a.name == "H"]
+    assert float(grad[:, outside].abs().max()) == 0.0
+    # (not the ideal frame: at rmsd ~ 1e-3 nm of fit residual the gradient is conditioned 1e4 worse)
+    sub = cvpack.BatchContext(system, x[10:14], precision=precision)
+    helpers.check_against_oracle(cv, system, x[10:14], None, precision, tol, tol * 5, context=sub)
+    # value only
+    only = cv.getValue(ctx)._value
+    assert torch.equal(only, value)
