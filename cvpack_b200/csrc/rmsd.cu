@@ -948,15 +948,21 @@ struct RmsdCV : cvp_cv {
       const dim3 grad_grid((unsigned)div_up(B, MULTI_TF), (unsigned)div_up(multi_n, MULTI_TA));
       static bool multi_configured = false;
       if (!multi_configured) {
-        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_gradient_kernel<RmsdSolution>,
+        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_gradient_kernel,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)MULTI_GRAD_SMEM));
         multi_configured = true;
       }
+      // the slice records are dead after the solve: their memory holds the W = factor * U^T records
+      double* weights = partials;
+      static_assert(sizeof(double) * 10 <= sizeof(double) * 13, "W records fit the slice records");
+      rmsd_multi_weights_kernel<RmsdSolution><<<(unsigned)div_up(B * num_groups, 256), 256, 0, st>>>(
+          solution, group_factor, B * (int64_t)num_groups, weights);
+      CVP_LAUNCH_CHECK();
       timer.begin("rmsd_multi_gradient", st);
-      rmsd_multi_gradient_kernel<RmsdSolution><<<grad_grid, MULTI_THREADS, MULTI_GRAD_SMEM, st>>>(
+      rmsd_multi_gradient_kernel<<<grad_grid, MULTI_THREADS, MULTI_GRAD_SMEM, st>>>(
           reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
-          static_cast<const double*>(d_ref.ptr), num_groups, B, solution, group_factor,
+          static_cast<const double*>(d_ref.ptr), num_groups, B, weights,
           seg_centroid, nseg, reinterpret_cast<float*>(grad), accumulate ? 1 : 0);
       timer.end(st);
       CVP_LAUNCH_CHECK();
@@ -1187,7 +1193,8 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
   // first + 1, ..., first + n - 1 in this order
   if (G >= 2 && cv->nseg == G && E % G == 0) {
     const int64_t n = E / G;
-    bool same = n >= 64;
+    // (the covariance kernel addresses a tile's rows with 32-bit offsets: 32 rows of 3 N values)
+    bool same = n >= 64 && (int64_t)desc->num_atoms * 3 * MULTI_TF < (int64_t(1) << 32);
     for (int g = 0; g < G && same; ++g) same = desc->group_offsets[g] == g * n;
     for (int64_t e = 0; e < E && same; ++e)
       same = cv->entry_atom[e] == cv->entry_atom[0] + (int32_t)(e % n);

@@ -30,8 +30,8 @@ constexpr int MULTI_THREADS = 256;
 constexpr int MULTI_TF = 32;      // frames per CTA tile
 constexpr int MULTI_TG = 32;      // groups per CTA tile (covariance)
 constexpr int MULTI_KA = 8;       // atoms per stage (covariance)
-constexpr int MULTI_TA = 64;      // atoms per CTA tile (gradient)
-constexpr int MULTI_KG = 16;      // groups per stage (gradient)
+constexpr int MULTI_TA = 128;     // atoms per CTA tile (gradient)
+constexpr int MULTI_KG = 8;       // groups per stage (gradient), two stages in flight
 
 // ---- covariance ----------------------------------------------------------------------------------
 // grid = (frame tiles, group tiles, SK); partials[(b * ns + g * SK + sk) * 13 + ...]
@@ -67,32 +67,42 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
   constexpr int ROW = MULTI_KA * 3;
   constexpr int NQ = MULTI_TF * ROW / MULTI_THREADS;
   static_assert(MULTI_TF * ROW % MULTI_THREADS == 0 && MULTI_TF == MULTI_TG, "loader shape");
+  static_assert(MULTI_TA == 128, "the gradient's Y stage layout assumes 16 threads x 8 atoms");
+  // (roles fixed per thread, so that a stage costs no index arithmetic: element q of this thread is
+  // value `rest` of row `row` -- a frame for X, a group for Y -- of the stage's 8 atoms x 3)
   float xr[NQ];
   double yr[NQ];
+  // 32-bit offsets from the tile's first frame / group (the host checks that they fit); an
+  // invalid row (frame or group beyond the end) is encoded as an atom index that is never in range
+  const float* x_base = pos + (f0 * num_atoms + first_atom) * 3;
+  const double* y_base = ref + (int64_t)g0 * n * 3;
+  uint32_t x_off[NQ], y_off[NQ];
+  int s_dst[NQ], a_rel_x[NQ], a_rel_y[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int idx = tid + q * MULTI_THREADS;
+    const int row = idx / ROW, rest = idx - row * ROW;
+    const int a = rest / 3, c = rest - a * 3;
+    s_dst[q] = (a * MULTI_TF + row) * 3 + c;
+    a_rel_x[q] = f0 + row < num_frames ? a : (1 << 30);
+    a_rel_y[q] = g0 + row < num_groups ? a : (1 << 30);
+    x_off[q] = (uint32_t)row * (uint32_t)(num_atoms * 3) + (uint32_t)rest;
+    y_off[q] = (uint32_t)row * (uint32_t)(n * 3) + (uint32_t)rest;
+  }
   auto load_regs = [&](int a0) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const int idx = tid + q * MULTI_THREADS;
-      const int row = idx / ROW, rest = idx - row * ROW;  // row: frame / group of the tile
-      const int a = a0 + rest / 3;
-      const int64_t f = f0 + row;
-      xr[q] = (f < num_frames && a < a_end)
-                  ? __ldg(pos + (f * num_atoms + first_atom) * 3 + (int64_t)a0 * 3 + rest)
-                  : 0.f;
-      const int g = g0 + row;
-      yr[q] = (g < num_groups && a < a_end)
-                  ? __ldg(ref + ((int64_t)g * n + a0) * 3 + rest)
-                  : 0.0;
+      xr[q] = a0 + a_rel_x[q] < a_end ? __ldg(x_base + x_off[q] + (int64_t)a0 * 3) : 0.f;
+      yr[q] = a0 + a_rel_y[q] < a_end ? __ldg(y_base + y_off[q] + (int64_t)a0 * 3) : 0.0;
     }
   };
   auto store_regs = [&](int buf) {
+    double* xs = &Xs[buf][0][0][0];
+    double* ys = &Ys[buf][0][0][0];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const int idx = tid + q * MULTI_THREADS;
-      const int row = idx / ROW, rest = idx - row * ROW;
-      const int a = rest / 3, c = rest - a * 3;
-      Xs[buf][a][row][c] = (double)xr[q];
-      Ys[buf][a][row][c] = yr[q];
+      xs[s_dst[q]] = (double)xr[q];
+      ys[s_dst[q]] = yr[q];
     }
   };
 
@@ -176,70 +186,135 @@ __global__ void rmsd_multi_moments_kernel(const float* __restrict__ pos, int64_t
 }
 
 // ---- gradient ------------------------------------------------------------------------------------
-// grid = (frame tiles, atom tiles).  `solution` / `factor` are indexed [frame][group].
+// W[f][g][0..8] = factor[f][g] * U^T[f][g], W[f][g][9] = factor[f][g]: one thread per (frame, group),
+// so that the W tiles of the gradient kernel are plain copies.
 template <typename Solution>
-__global__ void __launch_bounds__(MULTI_THREADS, 2)
+__global__ void rmsd_multi_weights_kernel(const Solution* __restrict__ solution,
+                                          const double* __restrict__ factor, int64_t total,
+                                          double* __restrict__ weights /* [frame][group][10] */) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const double fac = factor[t];
+  double2* out = reinterpret_cast<double2*>(weights + t * 10);
+  const double* ut = solution[t].ut;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out[k] = make_double2(fac * ut[2 * k], fac * ut[2 * k + 1]);
+  out[4] = make_double2(fac * ut[8], fac);
+}
+
+// 8- and 16-byte asynchronous copies global -> shared (LDGSTS); src_bytes = 0 fills with zeros
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr(smem_dst)),
+               "l"(gmem_src), "r"(valid ? 8 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(smem_dst)),
+               "l"(gmem_src), "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// grid = (frame tiles, atom tiles).  Groups in stages of MULTI_KG through a double-buffered
+// shared-memory ring filled by cp.async: the copies of stage k+1 are in flight while stage k is
+// multiplied (the synchronous version stalled on its tile loads: FP64 pipe 28 % busy).
+__global__ void __launch_bounds__(MULTI_THREADS, 1)
     rmsd_multi_gradient_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom,
                                int n, const double* __restrict__ ref, int num_groups,
-                               int64_t num_frames, const Solution* __restrict__ solution,
-                               const double* __restrict__ factor,
+                               int64_t num_frames, const double* __restrict__ weights,
                                const double* __restrict__ centroid /* [frame][nseg][3], seg 0 */,
                                int nseg, float* __restrict__ grad, int accumulate) {
   extern __shared__ __align__(16) double multi_smem[];
-  double (*Ws)[MULTI_TF][10] = reinterpret_cast<double (*)[MULTI_TF][10]>(multi_smem);  // f U^T, f
-  double (*Ys)[MULTI_TA][3] =
-      reinterpret_cast<double (*)[MULTI_TA][3]>(multi_smem + MULTI_KG * MULTI_TF * 10);
+  constexpr int W_STAGE = MULTI_KG * MULTI_TF * 10, Y_STAGE = MULTI_KG * MULTI_TA * 3;
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;  // frames 2ty, 2ty+1; atoms 4tx .. 4tx+3 of the tile
+  // thread tile 2 frames x 8 atoms: 42 doubles from shared memory per 144 DFMA.  (A 128-bit
+  // shared load costs 4 wavefronts, one per quarter warp, whatever is broadcast; with the 2 x 4
+  // tile ncu showed the shared-memory pipe 79 % busy and the FP64 pipe 41 %.)
+  const int ty = tid >> 4, tx = tid & 15;  // frames 2ty, 2ty+1; atoms 8tx .. 8tx+7 of the tile
   const int64_t f0 = (int64_t)blockIdx.x * MULTI_TF;
   const int a0 = blockIdx.y * MULTI_TA;
 
-  double acc[2][4][3];
+  // stage layout: Ws[gl][fl][10] (f U^T, f); Ys[gl]: the 24 doubles of thread tx (8 atoms x 3) as
+  // 12 double2 pieces, piece k at double2 index k * 16 + tx: a half-warp reads 256 contiguous
+  // bytes (in atom order the stride between threads is a multi-way bank conflict).
+  // Copy roles, fixed per thread so that a stage costs no index arithmetic:
+  //   W: thread -> (frame tid / MULTI_KG, group tid % MULTI_KG), its 80-byte record as 5 x 16 bytes;
+  //   Y: a group's tile row is 3 * MULTI_TA doubles; thread tid < 3 * MULTI_TA / 2 copies double2
+  //      `tid` of every group's row (n even: rows are 16-byte aligned), else two single doubles.
+  static_assert(MULTI_TF * MULTI_KG == MULTI_THREADS && 3 * MULTI_TA / 2 <= MULTI_THREADS, "copy roles");
+  const int w_fl = tid / MULTI_KG, w_gl = tid - w_fl * MULTI_KG;
+  const bool w_frame_ok = f0 + w_fl < num_frames;
+  const double* w_src = weights + ((w_frame_ok ? f0 + w_fl : 0) * num_groups + w_gl) * 10;
+  const int w_dst = (w_gl * MULTI_TF + w_fl) * 10;
+  const bool y_role = tid < 3 * MULTI_TA / 2;
+  const bool y_aligned = (n & 1) == 0;
+  // doubles 2 tid, 2 tid + 1 of the row: atoms (2 tid) / 3 and (2 tid + 1) / 3
+  const bool y_ok0 = y_role && a0 + (2 * tid) / 3 < n, y_ok1 = y_role && a0 + (2 * tid + 1) / 3 < n;
+  const double* y_src = ref + (int64_t)a0 * 3 + (y_ok0 ? 2 * tid : 0);
+  int y_dst = 0;
+  {
+    const int d = 2 * tid, owner = d / 24, q = d - owner * 24;  // (q even: both doubles in piece q / 2)
+    y_dst = ((q >> 1) * 16 + owner) << 1;
+  }
+  auto issue = [&](int g0, int buf) {
+    double* Ws = multi_smem + (size_t)buf * (W_STAGE + Y_STAGE);
+    double* Ys = Ws + W_STAGE;
+    {
+      const bool valid = w_frame_ok && g0 + w_gl < num_groups;
+      const double* src = valid ? w_src + (int64_t)g0 * 10 : weights;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) cp_async_16(Ws + w_dst + 2 * k, src + 2 * k, valid);
+    }
+    if (y_role) {
+#pragma unroll
+      for (int gl = 0; gl < MULTI_KG; ++gl) {
+        const bool group_ok = g0 + gl < num_groups;
+        const double* src = y_src + (int64_t)(g0 + gl) * n * 3;
+        double* dst = Ys + gl * (MULTI_TA * 3) + y_dst;
+        if (y_aligned) {
+          // (n even: 3 (n - a0) is even, so both doubles are valid or neither)
+          cp_async_16(dst, group_ok && y_ok0 ? src : ref, group_ok && y_ok0);
+        } else {
+          cp_async_8(dst, group_ok && y_ok0 ? src : ref, group_ok && y_ok0);
+          cp_async_8(dst + 1, group_ok && y_ok1 ? src + 1 : ref, group_ok && y_ok1);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  double acc[2][8][3];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int c = 0; c < 3; ++c) acc[i][j][c] = 0.0;
   double fsum[2] = {0.0, 0.0};
 
+  issue(0, 0);
+  int buf = 0;
   for (int g0 = 0; g0 < num_groups; g0 += MULTI_KG) {
-    __syncthreads();
-    // W tile: MULTI_KG groups x 32 frames, one (frame, group) pair per thread and pass; consecutive
-    // threads take consecutive groups of a frame (contiguous 80-byte solution records)
-    for (int idx = tid; idx < MULTI_KG * MULTI_TF; idx += MULTI_THREADS) {
-      const int fl = idx / MULTI_KG, gl = idx - fl * MULTI_KG;
-      const int g = g0 + gl;
-      const int64_t f = f0 + fl;
-      double w[10];
-      if (g < num_groups && f < num_frames) {
-        const double fac = factor[f * num_groups + g];
-        const Solution& sol = solution[f * num_groups + g];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) w[k] = fac * sol.ut[k];
-        w[9] = fac;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 10; ++k) w[k] = 0.0;
-      }
-#pragma unroll
-      for (int k = 0; k < 10; ++k) Ws[gl][fl][k] = w[k];
-    }
-    // Y tile: MULTI_KG groups x 64 atoms x 3 (192 contiguous doubles per group)
-    for (int idx = tid; idx < MULTI_KG * MULTI_TA * 3; idx += MULTI_THREADS) {
-      const int gl = idx / (MULTI_TA * 3), rest = idx - gl * (MULTI_TA * 3);
-      const int g = g0 + gl;
-      const int a = a0 + rest / 3;
-      (&Ys[gl][0][0])[rest] =
-          (g < num_groups && a < n) ? __ldg(ref + ((int64_t)g * n + a0) * 3 + rest) : 0.0;
+    const bool more = g0 + MULTI_KG < num_groups;
+    if (more) {
+      issue(g0 + MULTI_KG, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-#pragma unroll 2
+    const double* Ws = multi_smem + (size_t)buf * (W_STAGE + Y_STAGE);
+    const double* Ys = Ws + W_STAGE;
+#pragma unroll 1
     for (int gl = 0; gl < MULTI_KG; ++gl) {
       double w[2][10];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const double2* pw = reinterpret_cast<const double2*>(&Ws[gl][2 * ty + i][0]);
+        const double2* pw = reinterpret_cast<const double2*>(Ws + (gl * MULTI_TF + 2 * ty + i) * 10);
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const double2 v = pw[k];
@@ -248,24 +323,26 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
         }
         fsum[i] += w[i][9];
       }
-      const double2* py = reinterpret_cast<const double2*>(&Ys[gl][4 * tx][0]);
-      double y[12];
+      const double2* py = reinterpret_cast<const double2*>(Ys + gl * (MULTI_TA * 3)) + tx;
+      double y[24];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double2 v = py[k];
+      for (int k = 0; k < 12; ++k) {
+        const double2 v = py[k * 16];
         y[2 * k] = v.x;
         y[2 * k + 1] = v.y;
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
             acc[i][j][c] = fma(w[i][3 * c], y[3 * j],
                                fma(w[i][3 * c + 1], y[3 * j + 1],
                                    fma(w[i][3 * c + 2], y[3 * j + 2], acc[i][j][c])));
     }
+    __syncthreads();  // the stage is refilled by the copies issued in the next iteration
+    buf ^= 1;
   }
   // g = F (x - c) - acc
 #pragma unroll
@@ -277,8 +354,8 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
     const float* px = pos + (f * num_atoms + first_atom) * 3;
     float* pg = grad + (f * num_atoms + first_atom) * 3;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int a = a0 + 4 * tx + j;
+    for (int j = 0; j < 8; ++j) {
+      const int a = a0 + 8 * tx + j;
       if (a >= n) continue;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -293,7 +370,7 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
 }
 
 constexpr size_t MULTI_GRAD_SMEM =
-    sizeof(double) * (MULTI_KG * MULTI_TF * 10 + MULTI_KG * MULTI_TA * 3);
+    2 * sizeof(double) * (MULTI_KG * MULTI_TF * 10 + MULTI_KG * MULTI_TA * 3);
 
 }  // namespace
 }  // namespace cvp
