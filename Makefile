@@ -20,7 +20,7 @@ $(LIB): $(OBJECTS)
 oracle: oracle/liboracle.so
 
 oracle/liboracle.so: oracle/cv_oracle.c
-	gcc -O3 -march=native -fopenmp -fPIC -shared -o $@ $< -lm
+	gcc -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -o $@ $< -lm
 
 clean:
 	rm -rf build $(LIB) oracle/liboracle.so
