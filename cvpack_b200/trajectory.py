@@ -23,6 +23,7 @@ this module is host-side plumbing.
 
 from __future__ import annotations
 
+import concurrent.futures
 import io
 import math
 import os
@@ -83,8 +84,14 @@ class DCDFile:
         Whether every frame carries a unit-cell record.
     """
 
-    def __init__(self, path: t.Union[str, os.PathLike]) -> None:
+    def __init__(self, path: t.Union[str, os.PathLike], readThreads: t.Optional[int] = None) -> None:
         self.path = os.fspath(path)
+        if readThreads is None:
+            try:
+                readThreads = min(8, len(os.sched_getaffinity(0)))
+            except AttributeError:
+                readThreads = min(8, os.cpu_count() or 1)
+        self.readThreads = max(1, int(readThreads))
         with open(self.path, "rb") as file:
             head = file.read(92)
             if len(head) < 92 or struct.unpack("<i", head[:4])[0] != 84 or head[4:8] != b"CORD":
@@ -150,8 +157,20 @@ class DCDFile:
             raise ValueError("positions must be a float32 array of shape [count, numAtoms, 3]")
         block = self._map[start:start + count]
         scale = np.float32(_ANGSTROM_PER_NM)  # (a correctly rounded quotient, not x * 0.1f)
-        for k, axis in enumerate("xyz"):
-            np.divide(block[axis], scale, out=positions[:, :, k])
+
+        def convert(lo: int, hi: int) -> None:
+            for k, axis in enumerate("xyz"):
+                np.divide(block[axis][lo:hi], scale, out=positions[lo:hi, :, k])
+
+        # the strided de-interleave runs at about 1 GB/s per thread; numpy releases the GIL, so large
+        # chunks are split over a few threads (frames are independent)
+        workers = min(self.readThreads, count)
+        if workers > 1 and count * self.numAtoms >= (1 << 20):
+            bounds = np.linspace(0, count, workers + 1).astype(int)
+            with concurrent.futures.ThreadPoolExecutor(workers) as pool:
+                list(pool.map(lambda i: convert(int(bounds[i]), int(bounds[i + 1])), range(workers)))
+        else:
+            convert(0, count)
         boxes = None
         if self.hasBox:
             cell = np.asarray(block["cell"], dtype=np.float64)  # A, gamma, B, beta, alpha, C
@@ -319,6 +338,7 @@ class TrajectoryEvaluator:
         self._device = device
         self._precision = precision
         self._box = boxVectors
+        self._staging: t.Optional[t.Tuple[t.Any, t.List[torch.Tensor], t.List[torch.Tensor]]] = None
 
     # ---- table layout (reference: reporting/cv_writer.py:92-100) --------------------------------
     def getHeaders(self) -> t.List[str]:
@@ -372,8 +392,15 @@ class TrajectoryEvaluator:
             shared_box = self._box if self._box is not None else self._system.getDefaultPeriodicBoxVectors()
 
         depth = 2
-        host_pos = [torch.empty((chunk, num_atoms, 3), dtype=torch.float32, pin_memory=True) for _ in range(depth)]
-        host_box = [torch.empty((chunk, 3, 3), dtype=torch.float64, pin_memory=True) for _ in range(depth)]
+        # pinned staging is expensive to allocate (page locking): kept across calls
+        key = (chunk, num_atoms)
+        if self._staging is None or self._staging[0] != key:
+            self._staging = (
+                key,
+                [torch.empty((chunk, num_atoms, 3), dtype=torch.float32, pin_memory=True) for _ in range(depth)],
+                [torch.empty((chunk, 3, 3), dtype=torch.float64, pin_memory=True) for _ in range(depth)],
+            )
+        _, host_pos, host_box = self._staging
         with torch.cuda.device(device):
             dev_pos = [torch.empty((chunk, num_atoms, 3), dtype=torch.float32, device=device) for _ in range(depth)]
             dev_box = [torch.empty((chunk, 3, 3), dtype=torch.float64, device=device) for _ in range(depth)]

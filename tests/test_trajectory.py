@@ -38,6 +38,20 @@ def test_dcd_round_trip_without_box(tmp_path):
         dcd.read(4, 2)
 
 
+def test_dcd_threaded_read_equals_single_threaded(tmp_path):
+    rng = np.random.default_rng(10)
+    x = rng.uniform(-5, 5, size=(17, 70000, 3)).astype(np.float32)  # large enough to split
+    path = tmp_path / "big.dcd"
+    DCDFile.write(path, x)
+    one, _ = DCDFile(path, readThreads=1).read(0, 17)
+    many = DCDFile(path, readThreads=5)
+    assert many.readThreads == 5
+    got, _ = many.read(0, 17)
+    assert np.array_equal(one, got)
+    got, _ = many.read(3, 11)
+    assert np.array_equal(one[3:14], got)
+
+
 def test_dcd_header_layout_matches_the_format(tmp_path):
     """Byte-level check of the writer against the CHARMM layout OpenMM's DCDReporter emits."""
     path = tmp_path / "b.dcd"
