@@ -199,7 +199,7 @@ struct cvp_cv {
   cvp::KernelTimer timer;
   cvp::HostPipeline host;
   int device = -1;  // device the spec's arrays live on (-1: not uploaded yet)
-  int64_t workspace_limit = int64_t(1) << 30;
+  int64_t workspace_limit = int64_t(4) << 30;  // per spec and evaluate call (cvp_set_workspace_limit)
   std::vector<int32_t> active_atoms;  // sorted, unique
   cvp::DeviceBuffer workspace;
   virtual ~cvp_cv() {

@@ -808,7 +808,8 @@ struct RmsdCV : cvp_cv {
     return CVP_OK;
   }
   size_t workspace_per_frame(int, bool) const override {
-    return FusedLaunch<RmsdFusedPolicy>::workspace_per_frame((int)num_entries) +
+    // (the fused kernel's records only exist for the single contiguous group it serves)
+    return (fast ? FusedLaunch<RmsdFusedPolicy>::workspace_per_frame((int)num_entries) : 0) +
            (size_t)std::max(nslice, fast_nslice) * 13 * sizeof(double) + (size_t)num_groups * sizeof(RmsdSolution) +
            (size_t)nseg * 3 * sizeof(double) + (size_t)num_groups * sizeof(double) + 64;
   }

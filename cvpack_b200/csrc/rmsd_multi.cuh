@@ -31,6 +31,10 @@ constexpr int MULTI_TF = 32;      // frames per CTA tile
 constexpr int MULTI_TG = 32;      // groups per CTA tile (covariance)
 constexpr int MULTI_KA = 8;       // atoms per stage (covariance)
 constexpr int MULTI_TA = 128;     // atoms per CTA tile (gradient)
+#ifndef MULTI_GRAD_UNROLL
+#define MULTI_GRAD_UNROLL 1
+#endif
+constexpr int MULTI_GRAD_UNROLL_N = MULTI_GRAD_UNROLL;  // group steps unrolled in the gradient kernel
 constexpr int MULTI_KG = 8;       // groups per stage (gradient), two stages in flight
 
 // ---- covariance ----------------------------------------------------------------------------------
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1)
     __syncthreads();
     const double* Ws = multi_smem + (size_t)buf * (W_STAGE + Y_STAGE);
     const double* Ys = Ws + W_STAGE;
-#pragma unroll 1
+#pragma unroll MULTI_GRAD_UNROLL_N
     for (int gl = 0; gl < MULTI_KG; ++gl) {
       double w[2][10];
 #pragma unroll
@@ -331,15 +335,15 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1)
         y[2 * k] = v.x;
         y[2 * k + 1] = v.y;
       }
+      // (d outermost: 48 independent accumulators between two uses of the same one)
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+      for (int d = 2; d >= 0; --d)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            acc[i][j][c] = fma(w[i][3 * c], y[3 * j],
-                               fma(w[i][3 * c + 1], y[3 * j + 1],
-                                   fma(w[i][3 * c + 2], y[3 * j + 2], acc[i][j][c])));
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[i][j][c] = fma(w[i][3 * c + d], y[3 * j + d], acc[i][j][c]);
     }
     __syncthreads();  // the stage is refilled by the copies issued in the next iteration
     buf ^= 1;

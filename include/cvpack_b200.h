@@ -242,7 +242,7 @@ int cvp_version(void);
 int cvp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 /* Kernels launched by this library since the process started (all threads).                     */
 int64_t cvp_launch_count(void);
-/* Bytes of per-spec device workspace a spec may use per evaluate call (default 1 GiB).           */
+/* Bytes of per-spec device workspace a spec may use per evaluate call (default 4 GiB).           */
 int cvp_set_workspace_limit(cvp_cv* cv, int64_t bytes);
 /* Per-family tuning switch (meaning documented in DESIGN.md); returns previous value.            */
 int cvp_set_option(cvp_cv* cv, const char* name, int value);
