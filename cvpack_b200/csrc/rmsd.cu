@@ -614,7 +614,8 @@ __global__ void __launch_bounds__(BLOCKS_THREADS, 2)
     double v[13];
 #pragma unroll
     for (int k = 0; k < 13; ++k) v[k] = 0.0;
-    for (int e = begin; e < end; ++e) {
+#pragma unroll 6
+    for (int e = begin; e < end; ++e) {  // (unrolled: the slot loads of several entries in flight)
       const int slot = entry_slot[e];
       const double x = s_x[3 * slot], y = s_x[3 * slot + 1], z = s_x[3 * slot + 2];
       const double* r = shared_ref_entries ? s_ref + 3 * (e - begin) : ref + 3 * (int64_t)e;
