@@ -249,7 +249,8 @@ int cvp_set_option(cvp_cv* cv, const char* name, int value);
 /* Named statistic of a spec.  "<kernel>_ms" -> out[0] = device milliseconds spent in that kernel
  * since the last query (CUDA events on the launching stream; needs option "time_kernels" = 1),
  * out[1] = number of launches.  Kernel names: "sweep" (pair sums), "rmsd_sums", "rmsd_gradient",
- * "gyration_sums", "gyration_gradient".                                                         */
+ * "rmsd_fused", "rmsd_blocks", "rmsd_multi_cov", "rmsd_multi_gradient", "gyration_sums",
+ * "gyration_gradient", "gyration_fused".                                                        */
 int cvp_get_stat(cvp_cv* cv, const char* name, double* out);
 /* Sustained FP32 FMA throughput of `device` in TFLOP/s measured by a register-resident FFMA loop
  * (the FP32 roofline denominator of the pair kernels).                                           */
