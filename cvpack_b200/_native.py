@@ -155,9 +155,17 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     "cvp_bonded_create": (C.c_int, [C.POINTER(BondedDesc), C.POINTER(_vp)]),
     "cvp_destroy": (C.c_int, [_vp]),
     "cvp_active_atoms": (C.c_int, [_vp, _i32p, _i32p]),
+    "cvp_periodic_cutoff": (C.c_int, [_vp, _f64p]),
     "cvp_evaluate": (C.c_int, _eval_args + [_vp]),
     "cvp_evaluate_host": (C.c_int, _eval_args + [C.c_int]),
     "cvp_effective_mass": (C.c_int, [C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "cvp_evaluate_with_mass": (
+        C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int, _vp]
+    ),
+    "cvp_evaluate_with_mass_host": (
+        C.c_int,
+        [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int],
+    ),
     "cvp_path_cv_combine": (C.c_int, [C.POINTER(PathCVDesc), C.c_int, _vp, C.c_int64, _vp, _vp, _vp]),
     "cvp_axpy_frames": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp]),
     "cvp_last_error": (C.c_char_p, []),
@@ -264,6 +272,12 @@ class NativeCV:
         check(load().cvp_active_atoms(self._handle, C.byref(count), ptr_i32(atoms)))
         return atoms
 
+    def periodic_cutoff(self) -> float:
+        """Cutoff of a minimum-image sum (0 if the spec has none)."""
+        out = C.c_double()
+        check(load().cvp_periodic_cutoff(self._handle, C.byref(out)))
+        return out.value
+
     def set_workspace_limit(self, nbytes: int) -> None:
         """Cap the device workspace this spec may use per evaluate call."""
         check(load().cvp_set_workspace_limit(self._handle, int(nbytes)))
@@ -317,6 +331,31 @@ class NativeCV:
             load().cvp_evaluate_host(
                 self._handle, dtype, positions, box, box_mode, num_frames, num_atoms, value, grad,
                 flags, device,
+            )
+        )
+
+    def evaluate_with_mass(  # pylint: disable=too-many-arguments
+        self, dtype: int, positions: int, box: t.Optional[int], box_mode: int, num_frames: int,
+        num_atoms: int, masses: int, value: int, emass: int, flags: int, stream: int,
+    ) -> None:
+        """``cvp_evaluate_with_mass`` on device pointers: the gradient never leaves the library."""
+        check(
+            load().cvp_evaluate_with_mass(
+                self._handle, dtype, positions, box, box_mode, num_frames, num_atoms, masses, value,
+                emass, flags, stream,
+            )
+        )
+
+    def evaluate_with_mass_host(  # pylint: disable=too-many-arguments
+        self, dtype: int, positions: int, box: t.Optional[int], box_mode: int, num_frames: int,
+        num_atoms: int, masses: int, value: int, emass: int, grad: t.Optional[int], flags: int,
+        device: int,
+    ) -> None:
+        """``cvp_evaluate_with_mass_host`` on host pointers: only ``[B]`` results travel back."""
+        check(
+            load().cvp_evaluate_with_mass_host(
+                self._handle, dtype, positions, box, box_mode, num_frames, num_atoms, masses, value,
+                emass, grad, flags, device,
             )
         )
 

@@ -91,6 +91,7 @@ class BatchContext:
         self._box: t.Optional[torch.Tensor] = None
         self._box_mode = _native.CVP_BOX_NONE
         self._triclinic = False
+        self._half_min_edge = float("inf")
         self._compiled: t.Dict[int, t.Tuple[t.Any, _native.NativeCV]] = {}
         self._masses_dev: t.Optional[torch.Tensor] = None
         self._last: t.Dict[int, t.Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -176,6 +177,7 @@ class BatchContext:
         self._triclinic = bool((lower != 0).any())
         self._box_mode = _native.CVP_BOX_PER_FRAME if batched else _native.CVP_BOX_SHARED
         self._box_host = flat.clone()
+        self._half_min_edge = 0.5 * float(torch.diagonal(flat, dim1=1, dim2=2).min())
         self._box = self._place(tensor.reshape(-1, 9) if batched else tensor.reshape(9))
         self._last.clear()
 
@@ -234,6 +236,7 @@ class BatchContext:
         pos = self.getPositions() if positions is None else positions
         num_frames, num_atoms = int(pos.shape[0]), int(pos.shape[1])
         native = self._native_cv(cv)
+        self._check_cutoff(native)
         flags = _native.CVP_FLAG_TRICLINIC if self._triclinic else 0
         box_ptr = None if self._box is None else self._box.data_ptr()
         box_mode = self._box_mode if self._box is not None else _native.CVP_BOX_NONE
@@ -284,6 +287,18 @@ class BatchContext:
             )
         return value, grad
 
+    def _check_cutoff(self, native: _native.NativeCV) -> None:
+        """OpenMM refuses a periodic cutoff larger than half the smallest box edge; so do we (the
+        kernels would otherwise return a single-image sum silently)."""
+        if self._box is None:
+            return
+        cutoff = native.periodic_cutoff()
+        if cutoff > self._half_min_edge:
+            raise ValueError(
+                "The cutoff distance cannot be greater than half the periodic box size "
+                f"(cutoff {cutoff:g} nm, smallest box edge {2 * self._half_min_edge:g} nm)."
+            )
+
     def _check_out(
         self,
         out: t.Tuple[torch.Tensor, t.Optional[torch.Tensor]],
@@ -331,19 +346,60 @@ class BatchContext:
         return float(value[0])
 
     def _effectiveMass(self, cv: t.Any) -> torch.Tensor:
-        _, grad = self._run(cv, True)
-        assert grad is not None
+        """
+        ``1/sum_i |g_i|^2/m_i`` per frame (``utils.py:151-184``).  The ``[B, N, 3]`` gradient is an
+        intermediate: it lives in a library-owned scratch buffer on the device and only ``[B]``
+        numbers come back -- on a host-resident context nothing but the coordinates crosses PCIe.
+        """
+        self._require_cuda()
+        if hasattr(cv, "_evaluateComposite"):
+            # variables defined on other variables: gradient assembled by the composite, then reduced
+            _, grad = self._run(cv, True)
+            return self._massFromGradient(grad)
+        pos = self.getPositions()
+        num_frames, num_atoms = int(pos.shape[0]), int(pos.shape[1])
+        native = self._native_cv(cv)
+        self._check_cutoff(native)
+        flags = _native.CVP_FLAG_TRICLINIC if self._triclinic else 0
+        box_ptr = None if self._box is None else self._box.data_ptr()
+        box_mode = self._box_mode if self._box is not None else _native.CVP_BOX_NONE
+        if self._residency == "host":
+            masses = np.ascontiguousarray(self._system.getMasses(), dtype=np.float64)
+            value = torch.empty(num_frames, dtype=self._torch_dtype, pin_memory=True)
+            emass = torch.empty(num_frames, dtype=self._torch_dtype, pin_memory=True)
+            native.evaluate_with_mass_host(
+                self._cvp_dtype, pos.data_ptr(), box_ptr, box_mode, num_frames, num_atoms,
+                masses.ctypes.data, value.data_ptr(), emass.data_ptr(), None, flags,
+                self._device.index or 0,
+            )
+            return emass
         with torch.cuda.device(self._device):
-            if self._masses_dev is None:
-                self._masses_dev = torch.as_tensor(
-                    self._system.getMasses(), dtype=torch.float64, device=self._device
-                )
+            masses_dev = self._massesOnDevice()
+            value = torch.empty(num_frames, dtype=self._torch_dtype, device=self._device)
+            emass = torch.empty(num_frames, dtype=self._torch_dtype, device=self._device)
+            stream = torch.cuda.current_stream(self._device).cuda_stream
+            native.evaluate_with_mass(
+                self._cvp_dtype, pos.data_ptr(), box_ptr, box_mode, num_frames, num_atoms,
+                masses_dev.data_ptr(), value.data_ptr(), emass.data_ptr(), flags, stream,
+            )
+        return emass
+
+    def _massesOnDevice(self) -> torch.Tensor:
+        if self._masses_dev is None:
+            self._masses_dev = torch.as_tensor(
+                self._system.getMasses(), dtype=torch.float64, device=self._device
+            )
+        return self._masses_dev
+
+    def _massFromGradient(self, grad: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(self._device):
+            masses_dev = self._massesOnDevice()
             grad_dev = grad.to(self._device, non_blocking=True)
             num_frames, num_atoms = int(grad_dev.shape[0]), int(grad_dev.shape[1])
             out = torch.empty(num_frames, dtype=self._torch_dtype, device=self._device)
             stream = torch.cuda.current_stream(self._device).cuda_stream
             _native.effective_mass(
-                self._cvp_dtype, grad_dev.data_ptr(), self._masses_dev.data_ptr(), num_frames,
+                self._cvp_dtype, grad_dev.data_ptr(), masses_dev.data_ptr(), num_frames,
                 num_atoms, out.data_ptr(), stream,
             )
         return out.cpu() if self._residency == "host" else out

@@ -46,6 +46,23 @@ int prepare(cvp_cv* cv) {
 
 size_t elem_size(int dtype) { return dtype == CVP_F32 ? 4 : 8; }
 
+// Entry points that take a device ordinal switch to it for the duration of the call only: the
+// caller's current device (torch's, in the Python host) is restored on every return path.
+struct DeviceGuard {
+  int previous = -1;
+  cudaError_t status;
+  explicit DeviceGuard(int device) {
+    status = cudaGetDevice(&previous);
+    if (status == cudaSuccess && previous != device) status = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    int now = -1;
+    if (previous >= 0 && cudaGetDevice(&now) == cudaSuccess && now != previous) cudaSetDevice(previous);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int check_args(cvp_cv* cv, int dtype, const void* positions, int box_mode, int64_t B, int64_t N,
                void* value) {
   CVP_REQUIRE(cv != nullptr, "null spec");
@@ -103,6 +120,12 @@ int cvp_destroy(cvp_cv* cv) {
   return CVP_OK;
 }
 
+int cvp_periodic_cutoff(const cvp_cv* cv, double* cutoff) {
+  CVP_REQUIRE(cv != nullptr && cutoff != nullptr, "null argument");
+  *cutoff = cv->periodic_cutoff();
+  return CVP_OK;
+}
+
 int cvp_active_atoms(const cvp_cv* cv, int32_t* count, int32_t* atoms) {
   CVP_REQUIRE(cv != nullptr && count != nullptr, "null argument");
   *count = (int32_t)cv->active_atoms.size();
@@ -146,18 +169,26 @@ int cvp_evaluate(cvp_cv* cv, int dtype, const void* positions, const void* box, 
   return CVP_OK;
 }
 
+}  // extern "C"
+
+namespace {
 // Host-buffer path: frames flow through H2D copy -> kernels -> D2H copy in chunks; two slots so the
 // copies of one chunk overlap the kernels of the other (copy engines in both directions + SMs).
-int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
-                      int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,
-                      int device) {
+// With `masses` (host, double [N]) the effective mass of every frame is computed on the device
+// from the chunk's gradient and only [B] numbers travel back; `grad` may then be NULL.
+int evaluate_host_impl(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
+                       int64_t num_frames, int64_t num_atoms, void* value, void* grad,
+                       const double* masses, void* emass, int flags, int device) {
   int status = check_args(cv, dtype, positions, box_mode, num_frames, num_atoms, value);
   if (status != CVP_OK) return status;
   CVP_REQUIRE((flags & CVP_FLAG_ACCUMULATE) == 0, "accumulate is not supported on the host path");
+  CVP_REQUIRE((masses == nullptr) == (emass == nullptr), "masses and emass go together");
   if (num_frames == 0) return CVP_OK;
-  CVP_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  CVP_CUDA_CHECK(guard.status);
   const size_t es = elem_size(dtype);
-  const bool need_grad = grad != nullptr;
+  const bool copy_grad = grad != nullptr;
+  const bool need_grad = copy_grad || emass != nullptr;
   const size_t frame_bytes = (size_t)num_atoms * 3 * es;
   // chunk: at most ~256 MiB of coordinates, at least 1 frame, and >= 4 chunks when possible
   int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t(256) << 20) / frame_bytes));
@@ -171,6 +202,18 @@ int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* 
   };
   const auto t_start = now();
   const bool have_box = box != nullptr && box_mode != CVP_BOX_NONE;
+  if (have_box && cv->periodic_cutoff() > 0) {
+    // the boxes are host data here: refuse what OpenMM refuses (half the smallest edge < cutoff)
+    const int64_t boxes = box_mode == CVP_BOX_PER_FRAME ? num_frames : 1;
+    for (int64_t k = 0; k < boxes; ++k) {
+      double edge[3];
+      for (int a = 0; a < 3; ++a)
+        edge[a] = dtype == CVP_F32 ? (double)static_cast<const float*>(box)[9 * k + 4 * a]
+                                   : static_cast<const double*>(box)[9 * k + 4 * a];
+      CVP_REQUIRE(cv->periodic_cutoff() <= 0.5 * std::min(edge[0], std::min(edge[1], edge[2])),
+                  "The cutoff distance cannot be greater than half the periodic box size.");
+    }
+  }
   if ((status = hp.ensure()) != CVP_OK) return status;
   if (have_box && box_mode == CVP_BOX_SHARED) {
     if ((status = hp.shared_box.reserve(9 * es)) != CVP_OK) return status;
@@ -184,6 +227,13 @@ int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* 
     if (have_box && box_mode == CVP_BOX_PER_FRAME &&
         (status = hp.box[k].reserve((size_t)chunk * 9 * es)) != CVP_OK)
       return status;
+    if (emass != nullptr && (status = hp.emass[k].reserve((size_t)chunk * es)) != CVP_OK)
+      return status;
+  }
+  if (emass != nullptr) {
+    if ((status = hp.masses.reserve((size_t)num_atoms * sizeof(double))) != CVP_OK) return status;
+    CVP_CUDA_CHECK(cudaMemcpy(hp.masses.ptr, masses, (size_t)num_atoms * sizeof(double),
+                              cudaMemcpyHostToDevice));
   }
   // the spec's workspace is shared by both slots: kernels of consecutive chunks are serialised by
   // an event chain, copies are not
@@ -226,7 +276,15 @@ int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* 
     CVP_HOST_CHECK(cudaEventRecord(hp.kernels_done[k], stream));
     CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(value) + (size_t)first * es, hp.value[k].ptr,
                                    (size_t)count * es, cudaMemcpyDeviceToHost, stream));
-    if (need_grad)
+    if (emass != nullptr) {
+      status = effective_mass(dtype, hp.grad[k].ptr, static_cast<const double*>(hp.masses.ptr),
+                              count, num_atoms, hp.emass[k].ptr, stream);
+      if (status != CVP_OK) break;
+      CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(emass) + (size_t)first * es,
+                                     hp.emass[k].ptr, (size_t)count * es, cudaMemcpyDeviceToHost,
+                                     stream));
+    }
+    if (copy_grad)
       CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(grad) + (size_t)first * frame_bytes,
                                      hp.grad[k].ptr, (size_t)count * frame_bytes,
                                      cudaMemcpyDeviceToHost, stream));
@@ -244,6 +302,62 @@ int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* 
   }
   return status;
 #undef CVP_HOST_CHECK
+}
+}  // namespace
+
+extern "C" {
+
+int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
+                      int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,
+                      int device) {
+  return evaluate_host_impl(cv, dtype, positions, box, box_mode, num_frames, num_atoms, value, grad,
+                            nullptr, nullptr, flags, device);
+}
+
+int cvp_evaluate_with_mass_host(cvp_cv* cv, int dtype, const void* positions, const void* box,
+                                int box_mode, int64_t num_frames, int64_t num_atoms,
+                                const double* masses, void* value, void* emass, void* grad,
+                                int flags, int device) {
+  CVP_REQUIRE(masses != nullptr && emass != nullptr, "null masses or emass buffer");
+  return evaluate_host_impl(cv, dtype, positions, box, box_mode, num_frames, num_atoms, value, grad,
+                            masses, emass, flags, device);
+}
+
+// Value and effective mass on DEVICE buffers without materialising [B][N][3] for the caller: the
+// gradient of a slab of frames lives in a spec-owned scratch buffer (<= 1 GiB) between the CV
+// kernels and the effective-mass reduction.
+int cvp_evaluate_with_mass(cvp_cv* cv, int dtype, const void* positions, const void* box,
+                           int box_mode, int64_t num_frames, int64_t num_atoms,
+                           const double* masses, void* value, void* emass, int flags,
+                           void* stream) {
+  int status = check_args(cv, dtype, positions, box_mode, num_frames, num_atoms, value);
+  if (status != CVP_OK) return status;
+  CVP_REQUIRE(masses != nullptr && emass != nullptr, "null masses or emass buffer");
+  CVP_REQUIRE((flags & CVP_FLAG_ACCUMULATE) == 0, "accumulate is not supported with effective mass");
+  if (num_frames == 0) return CVP_OK;
+  const size_t es = elem_size(dtype);
+  const size_t frame_bytes = (size_t)num_atoms * 3 * es;
+  const int64_t slab =
+      std::max<int64_t>(1, std::min<int64_t>(num_frames, (int64_t)((size_t(1) << 30) / frame_bytes)));
+  if ((size_t)slab * frame_bytes > cv->grad_scratch.bytes) {
+    if (cv->grad_scratch.ptr) CVP_CUDA_CHECK(cudaDeviceSynchronize());
+    if ((status = cv->grad_scratch.reserve((size_t)slab * frame_bytes)) != CVP_OK) return status;
+  }
+  for (int64_t first = 0; first < num_frames; first += slab) {
+    const int64_t count = std::min(slab, num_frames - first);
+    const void* fbox = box;
+    if (box != nullptr && box_mode == CVP_BOX_PER_FRAME)
+      fbox = static_cast<const char*>(box) + (size_t)first * 9 * es;
+    status = cvp_evaluate(cv, dtype, static_cast<const char*>(positions) + (size_t)first * frame_bytes,
+                          fbox, box_mode, count, num_atoms, static_cast<char*>(value) + (size_t)first * es,
+                          cv->grad_scratch.ptr, flags, stream);
+    if (status != CVP_OK) return status;
+    status = effective_mass(dtype, cv->grad_scratch.ptr, masses, count, num_atoms,
+                            static_cast<char*>(emass) + (size_t)first * es,
+                            static_cast<cudaStream_t>(stream));
+    if (status != CVP_OK) return status;
+  }
+  return CVP_OK;
 }
 
 int cvp_effective_mass(int dtype, const void* grad, const double* masses, int64_t num_frames,
@@ -296,7 +410,8 @@ int cvp_get_stat(cvp_cv* cv, const char* name, double* out) {
 
 int cvp_measure_fp32_peak(int device, double* tflops) {
   CVP_REQUIRE(tflops != nullptr, "null argument");
-  CVP_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  CVP_CUDA_CHECK(guard.status);
   return measure_fp32_peak(tflops);
 }
 

@@ -75,6 +75,12 @@ int upload(DeviceBuffer& buffer, const std::vector<U>& host) {
   return CVP_OK;
 }
 
+// The vectorised (float4) and TMA bulk paths need 16-byte aligned base addresses; a C-ABI caller or a
+// tensor view with a storage offset may hand in less (null counts as aligned).
+inline bool aligned16(const void* a, const void* b = nullptr) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
+}
+
 // Linear carve-up of a workspace allocation (256-byte aligned pieces).
 struct Carver {
   char* base;
@@ -162,7 +168,7 @@ namespace cvp {
 // as long as the spec so that repeated calls neither allocate nor free device memory.
 struct HostPipeline {
   static constexpr int SLOTS = 2;
-  DeviceBuffer pos[SLOTS], grad[SLOTS], value[SLOTS], box[SLOTS], shared_box;
+  DeviceBuffer pos[SLOTS], grad[SLOTS], value[SLOTS], box[SLOTS], emass[SLOTS], shared_box, masses;
   cudaStream_t stream[SLOTS] = {nullptr, nullptr};
   cudaEvent_t kernels_done[SLOTS] = {nullptr, nullptr};
   int ensure() {
@@ -188,8 +194,10 @@ struct HostPipeline {
       grad[k].release();
       value[k].release();
       box[k].release();
+      emass[k].release();
     }
     shared_box.release();
+    masses.release();
   }
 };
 }  // namespace cvp
@@ -202,16 +210,21 @@ struct cvp_cv {
   int64_t workspace_limit = int64_t(4) << 30;  // per spec and evaluate call (cvp_set_workspace_limit)
   std::vector<int32_t> active_atoms;  // sorted, unique
   cvp::DeviceBuffer workspace;
+  cvp::DeviceBuffer grad_scratch;  // cvp_evaluate_with_mass: gradients that never leave the library
   virtual ~cvp_cv() {
     timer.clear();
     host.release();
     workspace.release();
+    grad_scratch.release();
   }
   // Upload index/parameter arrays to the current device.
   virtual int upload() = 0;
   // Workspace bytes needed per frame and independent of the frame count.
   virtual size_t workspace_per_frame(int dtype, bool need_grad) const = 0;
   virtual size_t workspace_fixed(int dtype) const { return 0; }
+  // Cutoff of a sum that uses the minimum-image convention (0: none): OpenMM refuses to run such a
+  // force in a box whose smallest edge is less than twice the cutoff.
+  virtual double periodic_cutoff() const { return 0.0; }
   // Largest number of frames a single run() may be given.
   virtual int64_t max_frames_per_run() const { return 1 << 20; }
   // Evaluate frames [0, args.num_frames) of the given (already offset) pointers.
@@ -417,19 +430,22 @@ __device__ __forceinline__ void step_function(const StepParams& p, T x, T& s, T&
       ds = (dnum * den - num * dnum * (T(1) + T(2) * xn)) * inv * inv;
       break;
     }
-    default: {  // CVP_STEP_PLUMED
-      T xn1 = powi(x, p.n - 1), xm1 = powi(x, p.m - 1);
-      T num = T(1) - xn1 * x, den = T(1) - xm1 * x;
-      if (fabs((double)den) < 1e-6) {
-        // removable singularity at x = 1: Taylor expansion to first order
-        T r = T(p.n) / T(p.m);
-        s = r * (T(1) + T(0.5) * T(p.n - p.m) * (x - T(1)));
-        ds = r * T(0.5) * T(p.n - p.m);
-      } else {
-        T inv = T(1) / den;
-        s = num * inv;
-        ds = (-T(p.n) * xn1 * den + num * T(p.m) * xm1) * inv * inv;
+    default: {  // CVP_STEP_PLUMED: (1 - x^n)/(1 - x^m)
+      // Evaluated as the ratio of the geometric sums P_k(x) = 1 + x + ... + x^(k-1)
+      // ((1 - x^k) = (1 - x) P_k(x)): every term is positive for x >= 0, so there is neither the
+      // removable singularity at x = 1 nor the cancellation of the literal form around it (which
+      // costs FP32 three digits at |x - 1| ~ 1e-4).  Horner with the derivative carried along.
+      const int hi = p.n > p.m ? p.n : p.m;
+      T poly = T(1), dpoly = T(0), pn = T(1), dpn = T(0), pm = T(1), dpm = T(0);
+      for (int k = 2; k <= hi; ++k) {
+        dpoly = fma(dpoly, x, poly);
+        poly = fma(poly, x, T(1));
+        if (k == p.n) { pn = poly; dpn = dpoly; }
+        if (k == p.m) { pm = poly; dpm = dpoly; }
       }
+      const T inv = T(1) / pm;
+      s = pn * inv;
+      ds = (dpn * pm - pn * dpm) * inv * inv;
       break;
     }
   }

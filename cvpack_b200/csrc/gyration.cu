@@ -500,7 +500,7 @@ struct GyrationCV : cvp_cv {
 
     // streaming fast path: FP32, no box, contiguous group starting on a 16-byte boundary
     const bool use_fast = PBC == 0 && std::is_same<T, float>::value && contiguous && n % 4 == 0 &&
-                          first % 4 == 0 && N % 4 == 0;
+                          first % 4 == 0 && N % 4 == 0 && aligned16(a.positions, a.grad);
     const int fast_ns = (int)div_up(n, GYR_FAST_SLICE);
     const float* wf = uniform_weights ? nullptr : static_cast<const float*>(d_weights_f32.ptr);
     if (use_fast && use_fused && B >= 64) {

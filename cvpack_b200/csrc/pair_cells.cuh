@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
                       const typename Vec4<T>::type* __restrict__ jaabb,
                       const typename Vec4<T>::type* __restrict__ atom_params, int ni_pad, int nj_pad,
                       int nsplit, const T* __restrict__ box, int box_mode, PairConsts<T> pc,
-                      const T* __restrict__ frame_coef, double* __restrict__ energy_partials,
+                      const typename PairFn<T, KIND>::Acc* __restrict__ frame_coef,
+                      double* __restrict__ energy_partials,
                       typename Vec4<T>::type* __restrict__ igrad,
                       typename Vec4<T>::type* __restrict__ jgrad = nullptr, float sym_scale = 0.f,
                       int sym_passes = 1) {
@@ -364,7 +365,8 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
     half_box[2] = T(0.5) * bx.cz;
   }
   const T rc = sqrt_t(pc.cutoff2);
-  const T* fc = (KIND == CVP_PAIR_SOFTMIN && GRAD) ? frame_coef + 2 * b : nullptr;
+  using Acc = typename Fn::Acc;
+  const Acc* fc = (KIND == CVP_PAIR_SOFTMIN && GRAD) ? frame_coef + 2 * b : nullptr;
 
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -372,9 +374,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   }
   __syncthreads();
 
-  T en[NCH];
+  Acc en[NCH];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) en[c] = T(0);
+  for (int c = 0; c < NCH; ++c) en[c] = Acc(0);
 
   uint32_t phase = 0;
   for (int j0 = 0; j0 < nj_pad; j0 += jchunk) {
@@ -523,9 +525,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               if (tagi & tagj & TAG_BOTH) w = T(0.5);
             }
             if (ok) {
-              T e[NCH];
+              Acc e[NCH];
               T coef;
-              if (FAST6) {
+              if constexpr (FAST6) {
                 contacts_rational6(pc, r2, e[0], coef);
               } else {
                 T4 qj;
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
                 Fn::eval(pc, r2, qi, qj, fc, e, coef);
               }
 #pragma unroll
-              for (int c = 0; c < NCH; ++c) en[c] += w * e[c];
+              for (int c = 0; c < NCH; ++c) en[c] += Acc(w) * e[c];
               if (GRAD) {
                 coef *= w;
                 const T fx = coef * dx, fy = coef * dy, fz = coef * dz;

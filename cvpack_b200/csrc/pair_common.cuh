@@ -85,7 +85,8 @@ __device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
 // only r^2 (x^6 = (r^2/r0^2)^3); branch-free switching.
 template <typename T>
 __device__ __forceinline__ void contacts_rational6(const PairConsts<T>& pc, T r2, T& e, T& coef) {
-  const T inv_r = fast_rsqrt(r2);
+  // r2 == 0 (coincident atoms): S(0) = 1 and no force, like the reference; avoids 0 * inf
+  const T inv_r = r2 > T(0) ? fast_rsqrt(r2) : T(0);
   const T x2 = r2 * pc.inv_r0sq;
   const T x6 = x2 * x2 * x2;
   const T s = fast_rcp(T(1) + x6);
@@ -113,10 +114,20 @@ struct PairFn;
 template <typename T>
 struct PairFn<T, CVP_PAIR_CONTACTS> {
   using T4 = typename Vec4<T>::type;
+  using Acc = T;  // type of the energy channels and of the per-frame coefficients
   static constexpr int NCH = 1;
   static constexpr bool HAS_PARAMS = false;
   __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4&, const T4&,
                                               const T*, T (&e)[1], T& coef) {
+    if (r2 == T(0)) {
+      // coincident atoms (or a residue listed in both groups of ResidueCoordination): the reference
+      // evaluates S(0) and a vanishing force; rsqrt(0) * 0 would be NaN
+      T s0, ds0;
+      step_function(pc.step, T(0), s0, ds0);
+      e[0] = s0;
+      coef = T(0);
+      return;
+    }
     T inv_r = fast_rsqrt(r2);
     T r = r2 * inv_r;
     T s, ds;
@@ -131,6 +142,7 @@ struct PairFn<T, CVP_PAIR_CONTACTS> {
 template <typename T>
 struct PairFn<T, CVP_PAIR_ATTRACTION> {
   using T4 = typename Vec4<T>::type;
+  using Acc = T;
   static constexpr int NCH = 1;
   static constexpr bool HAS_PARAMS = true;
   // params: x = charge, y = sigma, z = epsilon, w = sign
@@ -166,19 +178,22 @@ struct PairFn<T, CVP_PAIR_ATTRACTION> {
 template <typename T>
 struct PairFn<T, CVP_PAIR_SOFTMIN> {
   using T4 = typename Vec4<T>::type;
+  // The two channels sum r w and sum w, w = exp(-beta r/rc), and the per-frame quotient-rule
+  // coefficients {1/D, -rmin/D} are carried in double whatever T is: with the default beta = 100
+  // w spans e^-100 .. 1 and 1/D reaches e^100 -- beyond the range of FP32 -- while the products
+  // w/D <= 1 that enter the gradient are harmless.
+  using Acc = double;
   static constexpr int NCH = 2;
   static constexpr bool HAS_PARAMS = false;
-  // channels: sum r w and sum w, w = exp(-beta r/rc); gradient pass uses per-frame c = {1/D, -rmin/D}
   __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4&, const T4&,
-                                              const T* c, T (&e)[2], T& coef) {
+                                              const double* c, double (&e)[2], T& coef) {
     double r = sqrt((double)r2);
     double w = exp(pc.neg_beta_over_rc * r);
-    e[0] = T(r * w);
-    e[1] = T(w);
-    if (c != nullptr) {
-      // w and r w can underflow T; the normalised product w/D cannot overflow (w/D <= 1)
+    e[0] = r * w;
+    e[1] = w;
+    if (c != nullptr && r > 0.0) {
       double dw = pc.neg_beta_over_rc * w;
-      coef = T(((double)c[0] * (w + r * dw) + (double)c[1] * dw) / r);
+      coef = T((c[0] * (w + r * dw) + c[1] * dw) / r);
     } else {
       coef = T(0);
     }

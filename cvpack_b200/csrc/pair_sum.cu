@@ -62,10 +62,12 @@ __global__ void __launch_bounds__(PAIR_THREADS)
                       const typename Vec4<T>::type* __restrict__ iprm,
                       const typename Vec4<T>::type* __restrict__ jprm, int ni, int nj, int nblk_i,
                       const T* __restrict__ box, int box_mode, PairConsts<T> pc,
-                      const T* __restrict__ frame_coef, double* __restrict__ energy_partials,
+                      const typename PairFn<T, KIND>::Acc* __restrict__ frame_coef,
+                      double* __restrict__ energy_partials,
                       typename Vec4<T>::type* __restrict__ igrad) {
   using T4 = typename Vec4<T>::type;
   using Fn = PairFn<T, KIND>;
+  using Acc = typename Fn::Acc;
   constexpr int NCH = Fn::NCH;
   constexpr bool PRM = Fn::HAS_PARAMS;
 
@@ -110,11 +112,11 @@ __global__ void __launch_bounds__(PAIR_THREADS)
   T4 prmi[PAIR_IPT];
   bool valid[PAIR_IPT];
   T gx[PAIR_IPT], gy[PAIR_IPT], gz[PAIR_IPT];
-  T en[PAIR_IPT][NCH];
+  Acc en[PAIR_IPT][NCH];
 #pragma unroll
   for (int k = 0; k < PAIR_IPT; ++k) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) en[k][c] = T(0);
+    for (int c = 0; c < NCH; ++c) en[k][c] = Acc(0);
     int i = ib * PAIR_I_PER_BLOCK + k * PAIR_THREADS + tid;
     valid[k] = i < ni;
     if (!valid[k]) i = ni - 1;
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(PAIR_THREADS)
     if (PRM) prmi[k] = iprm[i];
     gx[k] = gy[k] = gz[k] = T(0);
   }
-  const T* fc = (KIND == CVP_PAIR_SOFTMIN && GRAD) ? frame_coef + 2 * b : nullptr;
+  const Acc* fc = (KIND == CVP_PAIR_SOFTMIN && GRAD) ? frame_coef + 2 * b : nullptr;
 
   for (int tile = 0; tile < ntile; ++tile) {
     const int s = tile & 1;
@@ -149,11 +151,11 @@ __global__ void __launch_bounds__(PAIR_THREADS)
             if (((tagi[k] ^ tagj) & TAG_INDEX_MASK) == 0) continue;  // same atom
             if (tagi[k] & tagj & TAG_BOTH) w = T(0.5);               // pair seen from both sides
           }
-          T e[NCH];
+          Acc e[NCH];
           T coef;
           Fn::eval(pc, r2, prmi[k], qj, fc, e, coef);
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) en[k][c] += w * e[c];
+          for (int c = 0; c < NCH; ++c) en[k][c] += Acc(w) * e[c];
           if (GRAD) {
             coef *= w;
             gx[k] -= coef * dx;
@@ -232,7 +234,7 @@ __global__ void exclusion_gradient_kernel(const T* __restrict__ pos, int64_t num
     if (r2 < pc.cutoff2) {
       T4 qp;
       if (Fn::HAS_PARAMS) qp = atom_params[p];
-      T en[Fn::NCH];
+      typename Fn::Acc en[Fn::NCH];
       T coef;
       Fn::eval(pc, r2, qa, qp, nullptr, en, coef);
       gx -= coef * dx;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(128)
         qa = atom_params[a];
         qp = atom_params[p];
       }
-      T en[Fn::NCH];
+      typename Fn::Acc en[Fn::NCH];
       T coef;
       Fn::eval(pc, r2, qa, qp, nullptr, en, coef);
       v[0] += (double)en[0];
@@ -290,7 +292,8 @@ template <typename T, int KIND>
 __global__ void pair_finish_kernel(const double* __restrict__ partials, int nblk,
                                    const double* __restrict__ excluded, double scale,
                                    double rc, double exp_neg_beta, T* __restrict__ value,
-                                   T* __restrict__ frame_coef, int accumulate, int64_t num_frames) {
+                                   typename PairFn<T, KIND>::Acc* __restrict__ frame_coef,
+                                   int accumulate, int64_t num_frames) {
   constexpr int NCH = PairFn<T, KIND>::NCH;
   const int lane = threadIdx.x & 31;
   const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -308,8 +311,9 @@ __global__ void pair_finish_kernel(const double* __restrict__ partials, int nblk
     double denom = exp_neg_beta + sum[NCH - 1];
     result = (rc * exp_neg_beta + sum[0]) / denom;
     if (frame_coef != nullptr) {
-      frame_coef[2 * b] = T(1.0 / denom);
-      frame_coef[2 * b + 1] = T(-result / denom);
+      using Acc = typename PairFn<T, KIND>::Acc;
+      frame_coef[2 * b] = Acc(1.0 / denom);
+      frame_coef[2 * b + 1] = Acc(-result / denom);
     }
   } else {
     double e = sum[0];
@@ -360,6 +364,7 @@ struct PairSumCV : cvp_cv {
   }
 
   int nblk(int n) const { return (int)div_up(n, PAIR_I_PER_BLOCK); }
+  double periodic_cutoff() const override { return d.periodic && d.cutoff > 0 ? d.cutoff : 0.0; }
 
   template <typename T>
   int upload_params(int which) {
@@ -405,7 +410,7 @@ struct PairSumCV : cvp_cv {
     size_t bytes = n * rec + 2 * (n / CELL_CLUSTER) * rec + 1024;  // positions + cluster boxes
     if (need_grad) bytes += n * rec + 512;                         // packed gradients
     bytes += (size_t)std::max(nblk((int)g1.size()), 64) * 2 * sizeof(double);  // energy partials
-    bytes += sizeof(double) + 2 * real;                            // excluded energy, frame coef
+    bytes += sizeof(double) + 2 * sizeof(double) + 0 * real;       // excluded energy, frame coef
     return bytes;
   }
   int set_option(const char* name, int value) override {
@@ -548,7 +553,8 @@ struct PairSumCV : cvp_cv {
     T4* gr2 = need_grad ? carve.take<T4>((size_t)B * n2p) : nullptr;
     double* partials = carve.take<double>((size_t)B * nsplit * NCH);
     double* excluded = carve.take<double>((size_t)B);
-    T* frame_coef = carve.take<T>((size_t)B * 2);
+    using Acc = typename PairFn<T, KIND>::Acc;
+    Acc* frame_coef = carve.take<Acc>((size_t)B * 2);
     const T4* prm_atom = static_cast<const T4*>(d_prm_atom[which].ptr);
 
     {
@@ -575,7 +581,7 @@ struct PairSumCV : cvp_cv {
     float sym_scale = 0.f;
     int sym_passes = 1;
     const bool sym = sym_plan<T, KIND, OVERLAP>(need_grad, nsplit, n1p, &sym_scale, &sym_passes);
-    auto sweep = [&](bool first, bool with_grad, const T* coef, double* energy) -> int {
+    auto sweep = [&](bool first, bool with_grad, const Acc* coef, double* energy) -> int {
       const T4* ip = first ? s1 : s2;
       const T4* jp = first ? s2 : s1;
       const T4* jb = first ? bb2 : bb1;
@@ -679,7 +685,8 @@ struct PairSumCV : cvp_cv {
     const int nb1 = nblk(n1), nb2 = nblk(n2);
     double* partials = carve.take<double>((size_t)B * nb1 * NCH);
     double* excluded = carve.take<double>((size_t)B);
-    T* frame_coef = carve.take<T>((size_t)B * 2);
+    using Acc = typename PairFn<T, KIND>::Acc;
+    Acc* frame_coef = carve.take<Acc>((size_t)B * 2);
 
     const T4* prm1 = static_cast<const T4*>(d_prm1[which].ptr);
     const T4* prm2 = static_cast<const T4*>(d_prm2[which].ptr);
@@ -710,7 +717,7 @@ struct PairSumCV : cvp_cv {
     const int finish_blocks = (int)div_up(B * 32, 128);
 
     // one sweep: `first` selects which group sits in registers (true: group1 over group2)
-    auto sweep = [&](bool first, bool with_grad, const T* coef, double* energy) -> int {
+    auto sweep = [&](bool first, bool with_grad, const Acc* coef, double* energy) -> int {
       const T4* ip = first ? p1 : p2;
       const T4* jp = first ? p2 : p1;
       const T4* iq = first ? prm1 : prm2;

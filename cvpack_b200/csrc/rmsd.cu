@@ -874,7 +874,8 @@ struct RmsdCV : cvp_cv {
     double* group_factor = carve.take<double>((size_t)B * num_groups);
 
     // streaming fast path: FP32, one contiguous aligned group
-    const bool use_fast = fast && std::is_same<T, float>::value && (N % 4) == 0;
+    const bool use_fast = fast && std::is_same<T, float>::value && (N % 4) == 0 &&
+                          aligned16(a.positions, a.grad);
     FusedGeom geom;
     if (use_fast && use_fused && cp.mode == CVP_COMBINE_IDENTITY && B >= 64 &&
         FusedLaunch<RmsdFusedPolicy>::plan((int)num_entries, N, fast_first, B, grad != nullptr,

@@ -19,8 +19,16 @@
  *     cvp_last_error() gives the message of the last failure on the calling thread
  *   - the caller owns every buffer; the library owns only spec-internal device copies of index /
  *     parameter arrays and a per-spec workspace, both released by cvp_destroy
- *   - cvp_evaluate is asynchronous with respect to the host and ordered on `stream`; a spec must not
- *     be evaluated concurrently from two streams (its workspace is shared)
+ *   - cvp_evaluate is asynchronous with respect to the host and ordered on `stream`; a spec must be
+ *     evaluated on ONE stream / thread at a time: its workspace (and the staging buffers of the host
+ *     path) are shared by all calls on that spec.  Build one spec per stream for concurrency.
+ *   - alignment: any element-aligned pointer is accepted.  When `positions` and `grad` are both
+ *     16-byte aligned (every cudaMalloc / torch allocation is) and the group is a contiguous run
+ *     of atoms starting at a multiple of 4 in frames of a multiple of 4 atoms, RMSD and radius of
+ *     gyration take the vectorised / TMA streaming kernels; otherwise the generic kernels run --
+ *     same results to rounding, never a misaligned access.
+ *   - entry points taking a device ordinal (`*_host`, cvp_measure_fp32_peak) switch to that device
+ *     for the duration of the call and restore the caller's current device before returning
  */
 #ifndef CVPACK_B200_H
 #define CVPACK_B200_H
@@ -192,6 +200,13 @@ int cvp_destroy(cvp_cv* cv);
  * gathers across GPUs).  `atoms` may be NULL to query the count only.                             */
 int cvp_active_atoms(const cvp_cv* cv, int32_t* count, int32_t* atoms);
 
+/* Cutoff (nm) of a spec whose sum uses the minimum-image convention, 0 if it has none.  Like OpenMM
+ * ("The cutoff distance cannot be greater than half the periodic box size"), such a spec must only
+ * be evaluated in boxes whose smallest edge is at least twice this number: cvp_evaluate_host
+ * checks its (host) boxes and returns CVP_ERR_INVALID; for cvp_evaluate the boxes are device data
+ * and the check is the binding's (the Python host does it from its host copy of the box).        */
+int cvp_periodic_cutoff(const cvp_cv* cv, double* cutoff);
+
 /* Evaluate on DEVICE buffers, asynchronously on `stream` (a cudaStream_t; NULL = default stream).
  * `value` [B] and `grad` [B][N][3] have the coordinate type; `grad` may be NULL (value only).
  * Replaces Context.getState(getEnergy=True, getForces=True, groups=1<<g) per frame
@@ -211,6 +226,22 @@ int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* 
  * device, coordinate type.                                                                        */
 int cvp_effective_mass(int dtype, const void* grad, const double* masses, int64_t num_frames,
                        int64_t num_atoms, void* emass, void* stream);
+
+/* Value and effective mass in one call, without handing [B][N][3] to the caller: the gradient of a
+ * slab of frames stays in a spec-owned scratch buffer between the CV kernels and the reduction.
+ * Replaces CollectiveVariable.getEffectiveMass (collective_variable.py:237-309 ->
+ * utils.compute_effective_mass, utils.py:151-184).  Device buffers; `masses` [N] device double.   */
+int cvp_evaluate_with_mass(cvp_cv* cv, int dtype, const void* positions, const void* box,
+                           int box_mode, int64_t num_frames, int64_t num_atoms,
+                           const double* masses, void* value, void* emass, int flags,
+                           void* stream);
+
+/* Same through HOST buffers (`masses` [N] host double): only [B] values and [B] masses travel back;
+ * `grad` (host, [B][N][3]) may be NULL -- pass a buffer to get the gradient as well.  Synchronous. */
+int cvp_evaluate_with_mass_host(cvp_cv* cv, int dtype, const void* positions, const void* box,
+                                int box_mode, int64_t num_frames, int64_t num_atoms,
+                                const double* masses, void* value, void* emass, void* grad,
+                                int flags, int device);
 
 /* ---- PathInCVSpace: a path of milestones in the space of other collective variables ----------- */
 /* Replaces the CustomCVForce expression assembled by path_in_cv_space.py:141-158 and

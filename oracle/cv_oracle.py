@@ -315,7 +315,9 @@ def _pair_geometry(x, pairs, box, cutoff):
 
 def _scatter_pair_gradient(x, pairs, d, r, de):
     grad = np.zeros_like(x)
-    contrib = (de / r)[:, None] * d
+    # r == 0 (coincident atoms): the pair counts S(0) but its force direction d/r is undefined and
+    # d == 0 -- it contributes nothing (OpenMM's Reference platform would divide 0 by 0 here)
+    contrib = np.divide(de, r, out=np.zeros_like(r), where=r > 0)[:, None] * d
     np.add.at(grad, pairs[:, 1], contrib)
     np.add.at(grad, pairs[:, 0], -contrib)
     return grad
@@ -427,7 +429,7 @@ def residue_coordination(
     r = np.linalg.norm(d, axis=2)
     s, ds = step_function(step, r / r0, n, m)
     value = s.sum() / reference
-    coef = (ds / r0 / r / reference)[:, :, None] * d
+    coef = np.divide(ds / r0 / reference, r, out=np.zeros_like(r), where=r > 0)[:, :, None] * d
     g1 = -coef.sum(axis=1)
     g2 = coef.sum(axis=0)
     grad = np.zeros_like(x)

@@ -176,3 +176,147 @@ def test_quantity_inputs_and_units():
     assert torch.allclose(a._value, b._value, rtol=1e-6)
     assert a.unit.get_symbol() == "nm"
     assert torch.allclose(a.value_in_unit(mmunit.angstroms), 10 * a._value)
+
+
+# ---- round 2: advisor findings and boundary hygiene ------------------------------------------------
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("separation", [0.86, 0.93, 0.995, 1.2])
+def test_shortest_distance_near_and_beyond_the_cutoff(precision, separation):
+    """With beta = 100 the weights e^{-beta r/rc} fall below the FP32 range once r > 0.887 rc and
+    1/D above it: channels and quotient-rule coefficients are carried in double.  At 1.2 rc no pair
+    is inside the cutoff: the value is rc exactly and the gradient vanishes."""
+    rng = np.random.default_rng(61)
+    n = 80
+    system = helpers.make_system(n, rng)
+    x = rng.uniform(0.0, 0.3, size=(4, n, 3))
+    x[:, 40:, 0] += 0.3 + separation  # group 2 sits `separation` nm beyond the far face of group 1
+    cv = cvpack.ShortestDistance(range(40), range(40, 80), n, pbc=False)
+    vt, gt = (1e-5, 1e-5) if precision == "single" else (1e-10, 1e-10)
+    ctx = helpers.check_against_oracle(cv, system, x, None, precision, vt, gt)
+    value, grad = cv.getValueAndGradient(ctx)
+    assert torch.isfinite(value._value).all() and torch.isfinite(grad).all()
+    if separation > 1.0:
+        assert torch.all(value._value == 1.0) and not grad.any()
+
+
+def test_coincident_atoms_and_shared_residue_give_S0_not_nan():
+    """rsqrt(0)*0 is NaN: two atoms on top of each other count S(0) = 1 with no force, and a residue
+    listed in both groups of ResidueCoordination contributes S(0) (the reference evaluates it so)."""
+    rng = np.random.default_rng(62)
+    n = 64
+    box = np.diag([2.0, 2.0, 2.0])
+    system = helpers.make_system(n, rng, box)
+    x = rng.uniform(0, 2.0, size=(3, n, 3))
+    x[:, 40] = x[:, 3]  # atom 40 (group 2) coincides with atom 3 (group 1)
+    nb = helpers.make_nonbonded(n, rng, periodic=True)
+    for kwargs in ({}, {"stepFunction": "1/(1+x^4)"}):
+        cv = cvpack.NumberOfContacts(range(32), range(32, 64), nb, **kwargs)
+        helpers.check_against_oracle(cv, system, x, box, "single", 1e-5, 1e-5)
+    topology = helpers.make_peptide(8)
+    residues = list(topology.residues())
+    total = topology.getNumAtoms()
+    system = helpers.make_system(total, rng)
+    y = rng.uniform(0, 1.5, size=(2, total, 3))
+    cv = cvpack.ResidueCoordination(residues[:5], residues[4:], pbc=False, thresholdDistance=0.8)
+    ctx = helpers.check_against_oracle(cv, system, y, None, "single", 1e-5, 1e-5)
+    assert torch.isfinite(cv.getValue(ctx)._value).all()
+
+
+@pytest.mark.parametrize("offset_bytes", [4, 8, 12])
+def test_misaligned_buffers_take_the_generic_kernels(offset_bytes):
+    """A tensor view whose storage offset is not a multiple of 16 bytes must not reach the float4 /
+    TMA streaming kernels (sticky misaligned-address fault): same values from the generic path."""
+    rng = np.random.default_rng(63)
+    n, frames = 4096, 70
+    reference = rng.normal(size=(n, 3))
+    x = (reference[None] + 0.1 * rng.normal(size=(frames, n, 3))).astype(np.float32)
+    system = helpers.make_system(n, rng)
+    lib = _native.load()
+    shift = offset_bytes // 4
+    for cv in (cvpack.RMSD(reference, range(n), n), cvpack.RadiusOfGyration(range(n))):
+        cv.addToSystem(system)
+        ctx = cvpack.BatchContext(system, x)
+        value, grad = cv.getValueAndGradient(ctx)
+        native = ctx._native_cv(cv)
+        flat_pos = torch.empty(x.size + 4, dtype=torch.float32, device="cuda")
+        flat_grad = torch.empty(x.size + 4, dtype=torch.float32, device="cuda")
+        pos = flat_pos[shift:shift + x.size].view(frames, n, 3)
+        pos.copy_(torch.from_numpy(x))
+        out_grad = flat_grad[shift:shift + x.size].view(frames, n, 3)
+        out_value = torch.empty(frames, device="cuda")
+        assert pos.data_ptr() % 16 == offset_bytes
+        status = lib.cvp_evaluate(native.handle, _native.CVP_F32, pos.data_ptr(), None, 0, frames, n,
+                                  out_value.data_ptr(), out_grad.data_ptr(), 0, None)
+        assert status == 0, lib.cvp_last_error()
+        torch.cuda.synchronize()
+        assert torch.allclose(out_value, value._value, rtol=2e-6)
+        assert (out_grad - grad).abs().max() <= 2e-6 * grad.abs().max()
+
+
+def test_cutoff_larger_than_half_the_box_is_refused():
+    """OpenMM: 'The cutoff distance cannot be greater than half the periodic box size.'"""
+    rng = np.random.default_rng(64)
+    n = 100
+    system = helpers.make_system(n, rng)
+    x = rng.uniform(0, 1.0, size=(2, n, 3))
+    nb = helpers.make_nonbonded(n, rng, periodic=True)
+    cv = cvpack.NumberOfContacts(range(50), range(50, 100), nb)  # cutoff 0.6 nm
+    cv.addToSystem(system)
+    for box in (np.diag([1.1, 3.0, 3.0]), np.array([[[3.0, 0, 0], [0, 3.0, 0], [0, 0, 3.0]],
+                                                    [[3.0, 0, 0], [0, 1.19, 0], [0, 0, 3.0]]])):
+        for residency in ("device", "host"):
+            ctx = cvpack.BatchContext(system, x, box, residency=residency)
+            with pytest.raises(ValueError, match="cannot be greater than half the periodic box size"):
+                cv.getValue(ctx)
+    ctx = cvpack.BatchContext(system, x, np.diag([1.2, 1.2, 1.2]))  # exactly twice the cutoff is fine
+    assert torch.isfinite(cv.getValue(ctx)._value).all()
+    # the C ABI's host path checks its (host) boxes itself
+    native = ctx._native_cv(cv)
+    pos = torch.from_numpy(x.astype(np.float32)).pin_memory()
+    small = torch.tensor(np.diag([1.0, 3.0, 3.0]).ravel(), dtype=torch.float32)
+    value = torch.empty(2, dtype=torch.float32).pin_memory()
+    lib = _native.load()
+    status = lib.cvp_evaluate_host(native.handle, _native.CVP_F32, pos.data_ptr(), small.data_ptr(),
+                                   _native.CVP_BOX_SHARED, 2, n, value.data_ptr(), None, 0, 0)
+    assert status == -1 and b"half the periodic box size" in lib.cvp_last_error()
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_effective_mass_without_materialising_the_gradient(precision):
+    """getEffectiveMass goes through cvp_evaluate_with_mass[_host]: same numbers as the reduction of an
+    explicitly requested gradient, for both residencies, without a [B,N,3] tensor on the Python side."""
+    rng = np.random.default_rng(65)
+    n = 300
+    box = np.diag([2.4, 2.4, 2.4])
+    system = helpers.make_system(n, rng)
+    x = rng.uniform(0, 2.4, size=(37, n, 3))
+    nb = helpers.make_nonbonded(n, rng, periodic=True, num_exceptions=10)
+    cvs = [cvpack.NumberOfContacts(range(150), range(150, 300), nb), cvpack.RadiusOfGyration(range(20, 200)),
+           cvpack.Torsion(1, 5, 9, 13)]
+    for cv in cvs:
+        cv.addToSystem(system)
+    masses = system.getMasses()
+    for residency in ("device", "host"):
+        ctx = cvpack.BatchContext(system, x, box, precision=precision, residency=residency)
+        for cv in cvs:
+            emass = cv.getEffectiveMass(ctx)
+            assert emass._value.shape == (37,) and emass._value.is_cuda == (residency == "device")
+            grad = cv.getGradient(ctx).double().cpu().numpy()
+            expected = [oracle.effective_mass(grad[b], masses) for b in range(37)]
+            assert np.allclose(emass._value.double().cpu().numpy(), expected,
+                               rtol=1e-5 if precision == "single" else 1e-12)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two devices")
+def test_host_path_restores_the_current_device():
+    rng = np.random.default_rng(66)
+    n = 40
+    system = helpers.make_system(n, rng)
+    cv = cvpack.RadiusOfGyration(range(n))
+    cv.addToSystem(system)
+    torch.cuda.set_device(0)
+    ctx = cvpack.BatchContext(system, rng.normal(size=(3, n, 3)), device="cuda:1", residency="host")
+    cv.getValue(ctx)
+    assert torch.cuda.current_device() == 0
+    _native.measure_fp32_peak(1)
+    assert torch.cuda.current_device() == 0
