@@ -19,6 +19,7 @@ from .helix_angle_content import HelixAngleContent  # noqa: F401
 from .helix_hbond_content import HelixHBondContent  # noqa: F401
 from .helix_rmsd_content import HelixRMSDContent  # noqa: F401
 from .helix_torsion_content import HelixTorsionContent  # noqa: F401
+from .meta_collective_variable import MetaCollectiveVariable  # noqa: F401
 from .mm import NonbondedForce, System, Vec3  # noqa: F401
 from .number_of_contacts import NumberOfContacts  # noqa: F401
 from .path_in_cv_space import PathInCVSpace  # noqa: F401
@@ -44,6 +45,7 @@ __all__ = [
     "HelixHBondContent",
     "HelixRMSDContent",
     "HelixTorsionContent",
+    "MetaCollectiveVariable",
     "NonbondedForce",
     "NumberOfContacts",
     "PathInCVSpace",

@@ -28,6 +28,16 @@ CVP_COMBINE_IDENTITY, CVP_COMBINE_STEP_SUM = 0, 1
 CVP_COMBINE_PATH_PROGRESS, CVP_COMBINE_PATH_DEVIATION = 2, 3
 CVP_TERM_IDENTITY, CVP_TERM_BOXCAR, CVP_TERM_HALF_COSINE = 0, 1, 2
 
+CVP_EXPR_MAX_OPS, CVP_EXPR_MAX_INPUTS, CVP_EXPR_MAX_TEMPS = 192, 16, 16
+CVP_EXPR_CONST, CVP_EXPR_INPUT, CVP_EXPR_LOAD, CVP_EXPR_STORE = 0, 1, 2, 3
+(CVP_EXPR_ADD, CVP_EXPR_SUB, CVP_EXPR_MUL, CVP_EXPR_DIV, CVP_EXPR_POW, CVP_EXPR_MIN, CVP_EXPR_MAX,
+ CVP_EXPR_ATAN2) = range(10, 18)
+CVP_EXPR_SELECT = 20
+(CVP_EXPR_NEG, CVP_EXPR_SQRT, CVP_EXPR_EXP, CVP_EXPR_LOG, CVP_EXPR_SIN, CVP_EXPR_COS, CVP_EXPR_TAN,
+ CVP_EXPR_SEC, CVP_EXPR_CSC, CVP_EXPR_COT, CVP_EXPR_ASIN, CVP_EXPR_ACOS, CVP_EXPR_ATAN, CVP_EXPR_SINH,
+ CVP_EXPR_COSH, CVP_EXPR_TANH, CVP_EXPR_ERF, CVP_EXPR_ERFC, CVP_EXPR_STEP, CVP_EXPR_DELTA,
+ CVP_EXPR_SQUARE, CVP_EXPR_CUBE, CVP_EXPR_RECIP, CVP_EXPR_ABS, CVP_EXPR_FLOOR, CVP_EXPR_CEIL) = range(30, 56)
+
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
 
@@ -144,6 +154,25 @@ class PathCVDesc(C.Structure):
     ]
 
 
+class ExprOp(C.Structure):
+    """``cvp_expr_op``"""
+
+    _fields_ = [("code", C.c_int32), ("arg", C.c_int32), ("value", C.c_double)]
+
+
+class ExprProgram(C.Structure):
+    """``cvp_expr_program``"""
+
+    _fields_ = [
+        ("num_ops", C.c_int32),
+        ("num_variables", C.c_int32),
+        ("num_parameters", C.c_int32),
+        ("reserved", C.c_int32),
+        ("parameters", C.c_double * CVP_EXPR_MAX_INPUTS),
+        ("ops", ExprOp * CVP_EXPR_MAX_OPS),
+    ]
+
+
 # every symbol include/cvpack_b200.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 _eval_args = [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int64, _vp, _vp, C.c_int]
@@ -167,6 +196,7 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
         [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, C.c_int],
     ),
     "cvp_path_cv_combine": (C.c_int, [C.POINTER(PathCVDesc), C.c_int, _vp, C.c_int64, _vp, _vp, _vp]),
+    "cvp_expr_eval": (C.c_int, [C.POINTER(ExprProgram), C.c_int, _vp, C.c_int64, _vp, _vp, _vp]),
     "cvp_axpy_frames": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp]),
     "cvp_last_error": (C.c_char_p, []),
     "cvp_version": (C.c_int, []),
@@ -382,6 +412,14 @@ def path_cv_combine(  # pylint: disable=too-many-arguments
         periods=ptr_f64(per), scales=ptr_f64(sca), sigma=float(sigma), metric=int(metric),
     )
     check(load().cvp_path_cv_combine(C.byref(desc), dtype, values, num_frames, out_value, out_coef, stream))
+
+
+def expr_eval(  # pylint: disable=too-many-arguments
+    program: ExprProgram, dtype: int, values: t.Optional[int], num_frames: int, out_value: int,
+    out_partial: t.Optional[int], stream: int,
+) -> None:
+    """``cvp_expr_eval`` on device pointers (``values``: ``[nv][B]``, ``out_partial``: ``[nv+np][B]``)."""
+    check(load().cvp_expr_eval(C.byref(program), dtype, values, num_frames, out_value, out_partial, stream))
 
 
 def axpy_frames(  # pylint: disable=too-many-arguments

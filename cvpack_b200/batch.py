@@ -95,6 +95,7 @@ class BatchContext:
         self._compiled: t.Dict[int, t.Tuple[t.Any, _native.NativeCV]] = {}
         self._masses_dev: t.Optional[torch.Tensor] = None
         self._last: t.Dict[int, t.Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._parameters: t.Dict[str, float] = {}
         if positions is not None:
             self.setPositions(positions)
         if boxVectors is None and system.getDefaultPeriodicBoxVectors() is not None:
@@ -180,6 +181,19 @@ class BatchContext:
         self._half_min_edge = 0.5 * float(torch.diagonal(flat, dim1=1, dim2=2).min())
         self._box = self._place(tensor.reshape(-1, 9) if batched else tensor.reshape(9))
         self._last.clear()
+
+    def setParameter(self, name: str, value: t.Any) -> None:
+        """Set a named global parameter (like ``openmm.Context.setParameter``); it overrides the default
+        of every :class:`MetaCollectiveVariable` parameter of that name."""
+        self._parameters[name] = float(value_in_md_units(value))
+
+    def getParameter(self, name: str, default: t.Any = None) -> float:
+        """Value of a named global parameter (``default`` if it was never set)."""
+        if name in self._parameters:
+            return self._parameters[name]
+        if default is None:
+            raise KeyError(f"Called getParameter() with invalid parameter name: {name}")
+        return float(default)
 
     def getPeriodicBoxVectors(self) -> t.Optional[torch.Tensor]:
         """Box vectors (``[9]`` or ``[B, 9]`` row-major) or None."""

@@ -13,6 +13,7 @@ import torch
 
 from . import _native, mmunit
 from .base_path_cv import BasePathCV
+from .composite import evaluate_composite
 from .collective_variable import CollectiveVariable
 from .path import Metric, progress
 from .units import value_in_md_units
@@ -120,50 +121,24 @@ class PathInCVSpace(BasePathCV):
         positions: t.Optional[torch.Tensor],
         out: t.Optional[t.Tuple[torch.Tensor, t.Optional[torch.Tensor]]],
     ) -> t.Tuple[torch.Tensor, t.Optional[torch.Tensor]]:
-        device = context.getDevice()
-        dtype = context._torch_dtype  # pylint: disable=protected-access
         cvp_dtype = context._cvp_dtype  # pylint: disable=protected-access
-        pos = context.getPositions() if positions is None else positions
-        with torch.cuda.device(device):
-            pos = pos.to(device).contiguous()
-            num_frames, num_atoms = int(pos.shape[0]), int(pos.shape[1])
-            nv = len(self._variables)
-            stream = torch.cuda.current_stream(device).cuda_stream
-            values = torch.empty((nv, num_frames), dtype=dtype, device=device)
-            for j, variable in enumerate(self._variables):
-                inner, _ = context._run(variable, False, positions=pos)  # pylint: disable=protected-access
-                values[j].copy_(inner)
-            value = torch.empty(num_frames, dtype=dtype, device=device)
-            coef = torch.empty((nv, num_frames), dtype=dtype, device=device) if need_gradient else None
-            metric = (
-                _native.CVP_COMBINE_PATH_PROGRESS
-                if self._metric == progress
-                else _native.CVP_COMBINE_PATH_DEVIATION
-            )
+        metric = (
+            _native.CVP_COMBINE_PATH_PROGRESS
+            if self._metric == progress
+            else _native.CVP_COMBINE_PATH_DEVIATION
+        )
+
+        def combine(values, out_value, out_partials, stream):
             _native.path_cv_combine(
                 self._milestones, self._periods, self._scales, self._sigma, metric, cvp_dtype,
-                values.data_ptr(), num_frames, value.data_ptr(),
-                None if coef is None else coef.data_ptr(), stream,
+                values.data_ptr(), int(values.shape[1]), out_value.data_ptr(),
+                None if out_partials is None else out_partials.data_ptr(), stream,
             )
-            grad = None
-            if need_gradient:
-                grad = torch.empty((num_frames, num_atoms, 3), dtype=dtype, device=device)
-                for j, variable in enumerate(self._variables):
-                    _, inner_grad = context._run(variable, True, positions=pos)  # pylint: disable=protected-access
-                    _native.axpy_frames(
-                        cvp_dtype, coef[j].data_ptr(), inner_grad.data_ptr(), grad.data_ptr(),
-                        num_frames, num_atoms, j > 0, stream,
-                    )
-                    del inner_grad
-        if out is not None:
-            out[0].copy_(value)
-            if need_gradient:
-                out[1].copy_(grad)
-            return out
-        if context._residency == "host" and positions is None:  # pylint: disable=protected-access
-            value = value.cpu().pin_memory()
-            grad = None if grad is None else grad.cpu().pin_memory()
-        return value, grad
 
+        # every inner variable is evaluated once, value and gradient together (composite.py)
+        value, grad, _, _ = evaluate_composite(
+            context, self._variables, combine, len(self._variables), need_gradient, positions, out
+        )
+        return value, grad
 
 PathInCVSpace.registerTag("!cvpack.PathInCVSpace")

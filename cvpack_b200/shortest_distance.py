@@ -67,7 +67,8 @@ class ShortestDistance(CollectiveVariable):
             group2=group2,
             numAtoms=numAtoms,
             beta=beta,
-            cutoffDistance=rc,
+            # (the reference registers the bare number it got from the quantity: `1`, not `1.0`)
+            cutoffDistance=value_in_md_units(cutoffDistance),
             pbc=pbc,
         )
 

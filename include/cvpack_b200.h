@@ -262,6 +262,47 @@ typedef struct {
 int cvp_path_cv_combine(const cvp_path_cv_desc* desc, int dtype, const void* values,
                         int64_t num_frames, void* out_value, void* out_coef, void* stream);
 
+/* ---- MetaCollectiveVariable: a function of other collective variables and named parameters ---- */
+/* Replaces the CustomCVForce of meta_collective_variable.py:114-141, whose energy function is a
+ * user-supplied Lepton expression of the inner variables' names and of named global parameters.
+ * The binding compiles that string into a postfix program (cvpack_b200/expression.py does, with
+ * Lepton's grammar); cvp_expr_eval interprets it for every frame: `values` [num_variables][B]
+ * (device, coordinate type) -> `out_value` [B] and, if not NULL, `out_partial`
+ * [num_variables + num_parameters][B] = d value / d input (inner variables first, then the
+ * parameters: meta_collective_variable.py:236-261 getParameterDerivatives).  cvp_axpy_frames then
+ * assembles the gradient.  Derivative rules at kinks are Lepton's (see csrc/expr.cu).           */
+enum { CVP_EXPR_MAX_OPS = 192, CVP_EXPR_MAX_INPUTS = 16, CVP_EXPR_MAX_TEMPS = 16 };
+enum {
+  CVP_EXPR_CONST = 0,   /* push `value`                                                            */
+  CVP_EXPR_INPUT = 1,   /* push input `arg` (inner variable, or parameter arg - num_variables)      */
+  CVP_EXPR_LOAD = 2,    /* push temporary slot `arg` (a `name = expression` definition)             */
+  CVP_EXPR_STORE = 3,   /* pop into temporary slot `arg`                                            */
+  CVP_EXPR_ADD = 10, CVP_EXPR_SUB, CVP_EXPR_MUL, CVP_EXPR_DIV, CVP_EXPR_POW, CVP_EXPR_MIN,
+  CVP_EXPR_MAX, CVP_EXPR_ATAN2,                                  /* binary: pop b, pop a, push a.b */
+  CVP_EXPR_SELECT = 20,                                          /* pop no, yes, cond              */
+  CVP_EXPR_NEG = 30, CVP_EXPR_SQRT, CVP_EXPR_EXP, CVP_EXPR_LOG, CVP_EXPR_SIN, CVP_EXPR_COS,
+  CVP_EXPR_TAN, CVP_EXPR_SEC, CVP_EXPR_CSC, CVP_EXPR_COT, CVP_EXPR_ASIN, CVP_EXPR_ACOS,
+  CVP_EXPR_ATAN, CVP_EXPR_SINH, CVP_EXPR_COSH, CVP_EXPR_TANH, CVP_EXPR_ERF, CVP_EXPR_ERFC,
+  CVP_EXPR_STEP, CVP_EXPR_DELTA, CVP_EXPR_SQUARE, CVP_EXPR_CUBE, CVP_EXPR_RECIP, CVP_EXPR_ABS,
+  CVP_EXPR_FLOOR, CVP_EXPR_CEIL                                  /* unary                          */
+};
+typedef struct {
+  int32_t code;
+  int32_t arg;
+  double value;
+} cvp_expr_op;
+typedef struct {
+  int32_t num_ops;
+  int32_t num_variables;
+  int32_t num_parameters;
+  int32_t reserved;
+  double parameters[CVP_EXPR_MAX_INPUTS];
+  cvp_expr_op ops[CVP_EXPR_MAX_OPS];
+} cvp_expr_program;
+
+int cvp_expr_eval(const cvp_expr_program* program, int dtype, const void* values,
+                  int64_t num_frames, void* out_value, void* out_partial, void* stream);
+
 /* y[b][N][3] = (accumulate ? y : 0) + coef[b] * x[b][N][3]; device buffers of the given dtype.   */
 int cvp_axpy_frames(int dtype, const void* coef, const void* x, void* y, int64_t num_frames,
                     int64_t num_atoms, int accumulate, void* stream);

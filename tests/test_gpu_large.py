@@ -299,7 +299,7 @@ def test_path_many_references_one_atom_set(metric, n_group, first, frames, miles
     ctx = cvpack.BatchContext(system, x)
     native = ctx._native_cv(cv)  # pylint: disable=protected-access
     native.set_option("time_kernels", 1)
-    helpers.check_against_oracle(cv, system, x, None, "single", 5e-5, 5e-5, context=ctx)
+    helpers.check_against_oracle(cv, system, x, None, "single", 1e-5, 1e-5, context=ctx)
     assert native.kernel_time("rmsd_multi_cov")[1] >= 1, "the multi-reference kernels did not run"
     value, grad = cv.getValueAndGradient(ctx)
     native.set_option("multi", 0)

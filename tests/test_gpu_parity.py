@@ -77,7 +77,7 @@ def test_path_in_cv_space(precision, metric):
                               scales=[1.0, 0.5 * mmunit.nanometers, 0.2])
     assert cv.getName() == f"path_{metric}_in_cv_space" and cv.getUnit().is_dimensionless()
     vt, gt = TOL[precision]
-    ctx = helpers.check_against_oracle(cv, system, x, None, precision, 5 * vt, 5 * gt)
+    ctx = helpers.check_against_oracle(cv, system, x, None, precision, vt, gt)
     emass = cv.getEffectiveMass(ctx)
     assert torch.isfinite(emass._value).all()  # pylint: disable=protected-access
     with pytest.raises(ValueError, match="Wrong number of columns"):
@@ -187,7 +187,7 @@ def test_attraction_strength(precision, boxname, contrast):
         reference=25.0 * mmunit.kilojoule_per_mole,
     )
     vt, gt = TOL[precision]
-    helpers.check_against_oracle(cv, system, x, box, precision, 4 * vt, 4 * gt)
+    helpers.check_against_oracle(cv, system, x, box, precision, vt, gt)
 
 
 @pytest.mark.parametrize("precision", ["single", "double"])
@@ -333,7 +333,7 @@ def test_path_in_rmsd_space(precision, metric):
     cv = cvpack.PathInRMSDSpace(getattr(cvpack.path, metric), milestones, n, 0.3 * mmunit.nanometers)
     assert cv.getName() == f"path_{metric}_in_rmsd_space"
     vt, gt = TOL[precision]
-    helpers.check_against_oracle(cv, system, x, None, precision, 5 * vt, 5 * gt)
+    helpers.check_against_oracle(cv, system, x, None, precision, vt, gt)
 
 
 @pytest.mark.parametrize("precision", ["single", "double"])
