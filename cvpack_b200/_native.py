@@ -206,6 +206,7 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     "cvp_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "cvp_get_stat": (C.c_int, [_vp, C.c_char_p, _f64p]),
     "cvp_measure_fp32_peak": (C.c_int, [C.c_int, _f64p]),
+    "cvp_measure_fp64_peak": (C.c_int, [C.c_int, _f64p]),
 }
 
 _lib: t.Optional[C.CDLL] = None
@@ -315,6 +316,12 @@ class NativeCV:
     def set_option(self, name: str, value: int) -> int:
         """Set a per-family tuning switch; returns the previous value (or -1 if unknown)."""
         return load().cvp_set_option(self._handle, name.encode(), int(value))
+
+    def stat(self, name: str) -> float:
+        """A named statistic of the spec (``cvp_get_stat``), e.g. ``"last_path"`` of a pair sum."""
+        out = (C.c_double * 2)()
+        check(load().cvp_get_stat(self._handle, name.encode(), out))
+        return float(out[0])
 
     def kernel_time(self, kernel: str) -> t.Tuple[float, int]:
         """(device milliseconds, launches) of a named kernel since the last query."""
@@ -439,6 +446,13 @@ def device_info(device: int = 0) -> t.Tuple[int, int, int]:
 def launch_count() -> int:
     """Kernels launched by the library since the process started."""
     return int(load().cvp_launch_count())
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    """Measured FP64 FMA throughput of a device in TFLOP/s."""
+    out = C.c_double()
+    check(load().cvp_measure_fp64_peak(device, C.byref(out)))
+    return out.value
 
 
 def measure_fp32_peak(device: int = 0) -> float:

@@ -20,6 +20,7 @@ int bonded_create(const cvp_bonded_desc*, cvp_cv**);
 int effective_mass(int dtype, const void* grad, const double* masses, int64_t B, int64_t N,
                    void* emass, cudaStream_t stream);
 int measure_fp32_peak(double* tflops);
+int measure_fp64_peak(double* tflops);
 
 namespace {
 
@@ -406,6 +407,13 @@ int cvp_get_stat(cvp_cv* cv, const char* name, double* out) {
   int status = cv->get_stat(name, out);
   if (status != CVP_OK) set_error(std::string("unknown statistic: ") + name);
   return status;
+}
+
+int cvp_measure_fp64_peak(int device, double* tflops) {
+  CVP_REQUIRE(tflops != nullptr, "null argument");
+  DeviceGuard guard(device);
+  CVP_CUDA_CHECK(guard.status);
+  return measure_fp64_peak(tflops);
 }
 
 int cvp_measure_fp32_peak(int device, double* tflops) {

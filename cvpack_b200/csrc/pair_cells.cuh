@@ -17,11 +17,14 @@
 //                                    (rsqrt, step function, switching, gradient) runs on real hits only.
 //   3. symmetric mode     (FP32 contacts with the default step function, disjoint groups, one CTA
 //                         per frame): a single sweep computes both sides of every pair.  The
-//                         gradient of the j atoms is accumulated in shared memory as 32-bit
-//                         fixed-point integers -- integer addition is associative, so the result
-//                         does not depend on the order of the atomics -- with a scale chosen on the
-//                         host such that even `passes`-th of the i atoms pushing one j atom in the
-//                         same direction with the largest possible |dE/dr| cannot overflow.
+//                         gradient of the j atoms is accumulated in shared memory in fixed point
+//                         -- integer addition is associative, so the result does not depend on the
+//                         order of the atomics.  The accumulator is a 32-bit word that is allowed
+//                         to wrap plus a wrap counter: every atomic add returns the old value, the
+//                         adding lane sees whether its own contribution crossed +-2^31 and, only
+//                         then, bumps the counter.  The sum is exact for any input, so the scale
+//                         (2^26 for the headline workload: a quantum of 1.5e-8) is set by the
+//                         size of one contribution, not by a worst-case bound on the sum.
 // Everything is deterministic: no floating-point atomics, fixed summation order per atom.
 #pragma once
 
@@ -81,11 +84,16 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
   // box of the grid: the periodic box, or the bounding box of the group in this frame
   T lo[3], len[3];
   if (PBC == 1) {
+    // the periodic cell is taken symmetric about the origin, [-L/2, L/2): wrapping into it never
+    // increases the magnitude of a coordinate, hence never coarsens its FP32 spacing (wrapping
+    // x = -0.15 nm to 15.85 nm in a 16 nm box would throw away five bits of every short distance)
     const Box<T> bx = load_box(box, box_mode, b);
-    lo[0] = lo[1] = lo[2] = T(0);
     len[0] = bx.ax;
     len[1] = bx.by;
     len[2] = bx.cz;
+    lo[0] = T(-0.5) * len[0];
+    lo[1] = T(-0.5) * len[1];
+    lo[2] = T(-0.5) * len[2];
   } else {
     T mn[3] = {T(3e38), T(3e38), T(3e38)}, mx[3] = {T(-3e38), T(-3e38), T(-3e38)};
     for (int i = tid; i < n; i += CELL_SORT_THREADS) {
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       T x = p[c];
-      if (PBC == 1) x = fma(-len[c], floor(x / len[c]), x);  // single rounding: exact k*L inside
+      if (PBC == 1) x = fma(-len[c], rint_t(x / len[c]), x);  // single rounding: exact k*L inside
       w[c] = x;
     }
   };
@@ -283,13 +291,21 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
 }
 
 // ---- 2. sweep ------------------------------------------------------------------------------------
+// survivor list of a warp: one 16-bit entry per cluster of the chunk that may hold a partner of the
+// tile -- cluster index within the chunk (8 bits), image code (2 bits per axis: 0 none, 1 +L,
+// 2 -L), unsafe flag
+constexpr int SURV_CAP = 256;  // = the most clusters a chunk may hold (cell_jchunk)
+constexpr uint32_t SURV_UNSAFE = 1u << 14;
+
 template <typename T>
 __host__ __device__ inline int cell_jchunk(bool sym = false) {
   // j atoms per shared-memory chunk: positions + (2 records per cluster of 8) within the budget;
-  // the symmetric mode adds 3 integer accumulators per atom and takes a little more room
+  // the symmetric mode adds 3 integer accumulators + 1 word of wrap counters per atom and takes a
+  // little more room
   const int per_atom =
-      (int)sizeof(typename Vec4<T>::type) * (CELL_CLUSTER + 2) / CELL_CLUSTER + (sym ? 12 : 0);
-  return ((sym ? CELL_SMEM_BUDGET_SYM : CELL_SMEM_BUDGET) / per_atom) / CELL_TILE * CELL_TILE;
+      (int)sizeof(typename Vec4<T>::type) * (CELL_CLUSTER + 2) / CELL_CLUSTER + (sym ? 16 : 0);
+  const int fit = ((sym ? CELL_SMEM_BUDGET_SYM : CELL_SMEM_BUDGET) / per_atom) / CELL_TILE * CELL_TILE;
+  return fit < SURV_CAP * CELL_CLUSTER ? fit : SURV_CAP * CELL_CLUSTER;
 }
 
 template <typename T>
@@ -298,14 +314,52 @@ __host__ __device__ inline size_t cell_sweep_smem(bool sym = false) {
   const int jchunk = cell_jchunk<T>(sym);
   const int batch_atoms = (sizeof(T) == 4 ? 16 : 8) * CELL_CLUSTER;
   return sizeof(T4) * ((size_t)jchunk + (size_t)(jchunk / CELL_CLUSTER) * 2 +
-                       (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms + 32)) +
-         (sym ? (size_t)jchunk * 3 * sizeof(int) : 0);
+                       (size_t)(CELL_SWEEP_THREADS / 32) * batch_atoms) +
+         (size_t)(CELL_SWEEP_THREADS / 32) * SURV_CAP * sizeof(uint16_t) +
+         (sym ? (size_t)jchunk * 4 * sizeof(int) : 0);
 }
 
-// fixed-point conversion of the symmetric mode: round(v * scale) for |v * scale| < 2^22, without
-// leaving the FMA/ALU pipes (the integer sits in the mantissa of v * scale + 1.5 * 2^23)
-__device__ __forceinline__ int sym_fixed(float v, float scale) {
-  return __float_as_int(fmaf(v, scale, 12582912.0f)) - 0x4B400000;
+// Symmetric mode: exact fixed-point accumulation.  x = round(v * scale) (F2I, |v * scale| < 2^30 by
+// the choice of the scale) is added to a 32-bit word that may wrap; the add returns the old value, so
+// the lane knows whether *its* contribution carried the sum across +-2^31 and then (rarely) moves
+// +-1 into the wrap counter of that component.  Three 10-bit counters, biased by 512, share one word
+// per atom: |wraps| <= scale * max|dE/dr| * n_i / 2^32 < 500 is part of the host's choice of scale.
+constexpr int SYM_WRAP_INIT = 512 | (512 << 10) | (512 << 20);
+#ifndef SYM_VARIANT
+#define SYM_VARIANT 0
+#endif
+__device__ __forceinline__ unsigned sym_fixed(float v, float scale) {
+#if SYM_VARIANT == 1 || SYM_VARIANT == 3
+  // |v * scale| < 2^22: the integer sits in the mantissa of v * scale + 1.5 * 2^23 (FMA pipe only)
+  return (unsigned)(__float_as_int(fmaf(v, scale, 12582912.0f)) - 0x4B400000);
+#else
+  return (unsigned)__float2int_rn(v * scale);
+#endif
+}
+__device__ __forceinline__ void sym_add3(int* lo, int* wraps, float vx, float vy, float vz, float scale) {
+  const unsigned x0 = sym_fixed(vx, scale), x1 = sym_fixed(vy, scale), x2 = sym_fixed(vz, scale);
+  unsigned* acc = reinterpret_cast<unsigned*>(lo);
+#if SYM_VARIANT >= 2
+  atomicAdd(acc, x0);
+  atomicAdd(acc + 1, x1);
+  atomicAdd(acc + 2, x2);
+#else
+  const unsigned o0 = atomicAdd(acc, x0), o1 = atomicAdd(acc + 1, x1), o2 = atomicAdd(acc + 2, x2);
+  const unsigned n0 = o0 + x0, n1 = o1 + x1, n2 = o2 + x2;
+  // signed overflow of a component: old and addend have the same sign, the new value the other one
+  const unsigned f0 = (o0 ^ n0) & (x0 ^ n0), f1 = (o1 ^ n1) & (x1 ^ n1), f2 = (o2 ^ n2) & (x2 ^ n2);
+  if ((int)(f0 | f1 | f2) < 0) {  // rare: one branch for the three components
+    int bump = 0;
+    if ((int)f0 < 0) bump += (int)x0 < 0 ? -1 : 1;
+    if ((int)f1 < 0) bump += ((int)x1 < 0 ? -1 : 1) << 10;
+    if ((int)f2 < 0) bump += ((int)x2 < 0 ? -1 : 1) << 20;
+    atomicAdd(wraps, bump);
+  }
+#endif
+}
+__device__ __forceinline__ float sym_value(int lo, int wraps, int component, float inv_scale) {
+  const int carry = ((wraps >> (10 * component)) & 1023) - 512;
+  return (float)(((double)carry * 4294967296.0 + (double)lo) * (double)inv_scale);
 }
 
 // grid = B * nsplit CTAs; CTA (b, part) owns the i tiles part, part + nsplit, ... (strided by warp).
@@ -342,8 +396,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   T4* jsm = reinterpret_cast<T4*>(sweep_smem);
   T4* bsm = jsm + jchunk;  // cluster boxes of the chunk: (centre, half) pairs
   T4* stage_all = bsm + (jchunk / CELL_CLUSTER) * 2;       // [NWARP][BATCH_ATOMS]
-  T4* survivors_all = stage_all + NWARP * BATCH_ATOMS;    // [NWARP][32]
-  int* jacc = reinterpret_cast<int*>(survivors_all + NWARP * 32);  // SYM: [jchunk][3]
+  T4* survivors_all = stage_all + NWARP * BATCH_ATOMS;    // [NWARP][SURV_CAP] 16-bit entries
+  int* jacc = reinterpret_cast<int*>(reinterpret_cast<uint16_t*>(survivors_all) + NWARP * SURV_CAP);  // SYM: [jchunk][3] wrapping sums
+  int* jwrap = jacc + 3 * jchunk;                                  // SYM: [jchunk] packed wrap counters
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t b = blockIdx.x / nsplit;
@@ -398,6 +453,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
     }
     if (SYM) {
       for (int a = tid; a < jcount * 3; a += CELL_SWEEP_THREADS) jacc[a] = 0;
+      for (int a = tid; a < jcount; a += CELL_SWEEP_THREADS) jwrap[a] = SYM_WRAP_INIT;
       __syncthreads();
     }
     mbar_wait(&bar, phase);
@@ -448,129 +504,18 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         ci[c] = T(0.5) * (mn[c] + mx[c]);
         hi[c] = T(0.5) * (mx[c] - mn[c]);
       }
+      const T4& pr = pi;  // the lane's atom as the pair loops see it
 
-      // A *batch* = up to BATCH_CL surviving clusters (128 atoms in FP32), copied -- already shifted
-      // to the right periodic image -- into this warp's staging buffer.  Phase 1 tests every staged
-      // atom against the lane's i atom and records hits in NW 32-bit masks; phase 2 lets every lane
-      // walk its own hits, so the expensive pair function runs for real contacts only.  The larger
-      // the batch, the closer the busiest lane is to the average one.
-      uint32_t hits[NW];
-#pragma unroll
-      for (int w = 0; w < NW; ++w) hits[w] = 0u;
-      int nbatch = 0;  // clusters staged so far
-      bool batch_unsafe = false;
-      T4* stg = stage_all + warp * BATCH_ATOMS;
-      T4* lst = survivors_all + warp * 32;
-      auto run_phases = [&](auto unsafe_tag) {
-        constexpr bool UNSAFE = decltype(unsafe_tag)::value;
-        auto test = [&](int slot) -> bool {
-          const T4 pj = stg[slot];
-          T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-          if (UNSAFE) pair_min_image<PBC>(dx, dy, dz, bx);
-          return fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2;
-        };
-        if (nbatch == BATCH_CL) {
-          // full batch: bit positions are compile-time constants
-#pragma unroll
-          for (int w = 0; w < NW; ++w) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u) {
-              if (test(w * 32 + u)) hits[w] |= 1u << u;
-            }
-          }
-        } else {
-          for (int c = 0; c < nbatch; ++c) {
-            uint32_t m = 0;
-#pragma unroll
-            for (int u = 0; u < CELL_CLUSTER; ++u) {
-              if (test(c * CELL_CLUSTER + u)) m |= 1u << u;
-            }
-            m <<= (c & 3) * CELL_CLUSTER;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-              if ((c >> 2) == w) hits[w] |= m;
-            }
-          }
-        }
-        int mine = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) mine += __popc(hits[w]);
-        const int rounds = __reduce_max_sync(FULL, mine);
-        for (int it = 0; it < rounds; ++it) {
-          int k = -1;
-#pragma unroll
-          for (int w = NW - 1; w >= 0; --w) {
-            if (hits[w] != 0u) k = w;
-          }
-          if (k >= 0) {
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-              if (k == w) {
-                k = w * 32 + __ffs(hits[w]) - 1;
-                hits[w] &= hits[w] - 1u;
-                break;
-              }
-            }
-            const T4 pj = stg[k];
-            const int tagj = tag_decode(pj.w);  // (SYM: the accumulator slot)
-            T dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-            if (UNSAFE) pair_min_image<PBC>(dx, dy, dz, bx);
-            const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            // padding never passes the shifted-image test (coordinates 1e18); the minimum-image
-            // reduction of the unsafe path can fold it back, so that path checks the tags
-            bool ok = UNSAFE ? (tagj >= 0 && tagi >= 0) : true;
-            T w = T(1);
-            if (OVERLAP) {
-              if (((tagi ^ tagj) & TAG_INDEX_MASK) == 0) ok = false;
-              if (tagi & tagj & TAG_BOTH) w = T(0.5);
-            }
-            if (ok) {
-              Acc e[NCH];
-              T coef;
-              if constexpr (FAST6) {
-                contacts_rational6(pc, r2, e[0], coef);
-              } else {
-                T4 qj;
-                if (PRM) qj = atom_params[tagj & TAG_INDEX_MASK];
-                Fn::eval(pc, r2, qi, qj, fc, e, coef);
-              }
-#pragma unroll
-              for (int c = 0; c < NCH; ++c) en[c] += Acc(w) * e[c];
-              if (GRAD) {
-                coef *= w;
-                const T fx = coef * dx, fy = coef * dy, fz = coef * dz;
-                gx -= fx;
-                gy -= fy;
-                gz -= fz;
-                if (SYM) {
-                  int* acc = jacc + tagj * 3;
-                  atomicAdd(acc, sym_fixed((float)fx, sym_scale));
-                  atomicAdd(acc + 1, sym_fixed((float)fy, sym_scale));
-                  atomicAdd(acc + 2, sym_fixed((float)fz, sym_scale));
-                }
-              }
-            }
-          }
-        }
-      };
-      auto run_batch = [&]() {
-        __syncwarp();
-        // the per-pair minimum image is needed only when some (tile, cluster) pair of the batch is
-        // too wide for a single shift; a warp-uniform branch keeps it out of the common path
-        if (PBC == 1 && batch_unsafe)
-          run_phases(std::true_type{});
-        else
-          run_phases(std::false_type{});
-        __syncwarp();
-        nbatch = 0;
-        batch_unsafe = false;
-      };
-
+      // ---- cull: all clusters of the chunk against the box of the tile ----
+      // Survivors go to this warp's list as (cluster, shift code, needs-minimum-image flag); the list
+      // is complete before anything is staged, because the batches below take their clusters from
+      // all over it.
+      uint16_t* lst = reinterpret_cast<uint16_t*>(survivors_all) + warp * SURV_CAP;
+      int nsurv = 0;
       for (int c0 = 0; c0 < ncl; c0 += 32) {
-        // ---- cull: lane l tests cluster c0 + l against the tile box ----
         const int c = c0 + lane;
         bool near = false, safe = true;
-        T sh[3] = {T(0), T(0), T(0)};
+        uint32_t code = 0u;
         if (c < ncl) {
           const T4 cj = bsm[2 * c], hj = bsm[2 * c + 1];
           const T cjv[3] = {cj.x, cj.y, cj.z}, hjv[3] = {hj.x, hj.y, hj.z};
@@ -580,8 +525,10 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           for (int a = 0; a < 3; ++a) {
             T d = cjv[a] - ci[a];
             if (PBC == 1) {
-              sh[a] = len[a] * rint_t(d / len[a]);
-              d -= sh[a];
+              // positions are wrapped into [-L/2, L/2]: the image count is -1, 0 or +1
+              const T k = rint_t(d / len[a]);
+              d -= k * len[a];
+              code |= (k > T(0) ? 1u : (k < T(0) ? 2u : 0u)) << (8 + 2 * a);
             }
             const T ext = hi[a] + hjv[a];
             const T gap = fmax(fabs(d) - ext, T(0));
@@ -592,42 +539,181 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           // clusters made of padding only sit at 1e18: the periodic shift would fold them back
           near = d2 < pc.cutoff2 && cj.x < T(1e17);
         }
-        // survivors of this window, compacted in cluster order: (shift, cluster index)
         const uint32_t cmask = __ballot_sync(FULL, near);
-        if (cmask == 0u) continue;
-        const bool window_unsafe = __any_sync(FULL, near && !safe);
-        if (near) {
-          T4 ent;
-          ent.x = sh[0];
-          ent.y = sh[1];
-          ent.z = sh[2];
-          ent.w = tag_encode(c, T(0));
-          lst[__popc(cmask & ((1u << lane) - 1u))] = ent;
-        }
-        __syncwarp();
-        const int nsurv = __popc(cmask);
-        for (int s0 = 0; s0 < nsurv;) {
-          const int take = min(BATCH_CL - nbatch, nsurv - s0);
-          // stage `take` clusters, 4 per pass (one atom per lane)
-          for (int a = lane; a < take * CELL_CLUSTER; a += 32) {
-            const T4 ent = lst[s0 + (a >> 3)];
-            T4 pj = jsm[tag_decode(ent.w) * CELL_CLUSTER + (a & 7)];
-            pj.x -= ent.x;  // d = (x_j - shift) - x_i is the minimum image for a safe cluster
-            pj.y -= ent.y;
-            pj.z -= ent.z;
-            if (SYM)  // the accumulator slot of the atom within the chunk (-1: padding)
-              pj.w = tag_encode(
-                  tag_decode(pj.w) < 0 ? -1 : tag_decode(ent.w) * CELL_CLUSTER + (a & 7), T(0));
-            stg[nbatch * CELL_CLUSTER + a] = pj;
-          }
-          batch_unsafe |= window_unsafe;
-          nbatch += take;
-          s0 += take;
-          if (nbatch == BATCH_CL) run_batch();
-        }
-        __syncwarp();  // the survivor list is rewritten by the next window
+        if (near)
+          lst[nsurv + __popc(cmask & ((1u << lane) - 1u))] =
+              (uint16_t)((uint32_t)c | code | (safe ? 0u : SURV_UNSAFE));
+        nsurv += __popc(cmask);
       }
-      if (nbatch > 0) run_batch();
+      __syncwarp();
+
+      // ---- batches ----
+      // A *batch* = BATCH_CL surviving clusters (128 atoms in FP32) copied -- already shifted to the
+      // right periodic image -- into this warp's staging buffer.  Phase 1 tests every staged atom
+      // against the lane's i atom and records hits in NW 32-bit masks; phase 2 lets every lane walk
+      // its own hits, so the expensive pair function runs for real contacts only and the j side is
+      // accumulated in shared memory.  Phase 2 lasts as long as its busiest lane: batch `b` of `nb`
+      // takes survivors b, b + nb, b + 2 nb, ... -- a sample of the whole neighbourhood of the tile
+      // instead of one corner of it -- so that every lane finds about the same number of hits in
+      // every batch (a batch of 16 *consecutive* clusters lies on one side of the tile: the lanes
+      // on that side had 2.3 x the average number of hits, ncu: 14 of 32 lanes active).
+      T4* stg = stage_all + warp * BATCH_ATOMS;
+      const int nb = (nsurv + BATCH_CL - 1) / BATCH_CL;
+      for (int bi = 0; bi < nb; ++bi) {
+        const int take = (nsurv - bi + nb - 1) / nb;  // <= BATCH_CL
+        bool unsafe = false;
+        for (int a = lane; a < BATCH_ATOMS; a += 32) {
+          T4 pj;
+          pj.x = pj.y = pj.z = T(1e18);  // padding of a short batch: never in range
+          pj.w = tag_encode(TAG_DUMMY, T(0));
+          if (a < take * CELL_CLUSTER) {
+            const uint32_t ent = lst[bi + (a >> 3) * nb];
+            const int cl = (int)(ent & 0xffu);
+            pj = jsm[cl * CELL_CLUSTER + (a & 7)];
+            if (PBC == 1) {
+              // d = (x_j - shift) - x_i is the minimum image for a safe cluster.  Same image (the
+              // common case): the stored coordinates go in as they are, so that x_j - x_i is the
+              // exact difference of the inputs -- steep pair functions (ShortestDistance: d ln w /
+              // d ln r = -100) feel every rounding of a coordinate.  Other image: x_j -+ L is formed
+              // in double and rounded once (x_j - L computed in FP32 from a wrapped coordinate may
+              // round twice); it lies near the tile, |.| <= L/2 + rc, so it is within
+              // ulp(L/2 + rc)/2 of the exact image.
+              const uint32_t kx = (ent >> 8) & 3u, ky = (ent >> 10) & 3u, kz = (ent >> 12) & 3u;
+              if ((kx | ky | kz) != 0u) {
+                const double sx = kx == 1u ? (double)bx.ax : (kx == 2u ? -(double)bx.ax : 0.0);
+                const double sy = ky == 1u ? (double)bx.by : (ky == 2u ? -(double)bx.by : 0.0);
+                const double sz = kz == 1u ? (double)bx.cz : (kz == 2u ? -(double)bx.cz : 0.0);
+                pj.x = T((double)pj.x - sx);
+                pj.y = T((double)pj.y - sy);
+                pj.z = T((double)pj.z - sz);
+              }
+              unsafe |= (ent & SURV_UNSAFE) != 0u;
+            }
+            if (SYM)  // the accumulator slot of the atom within the chunk (-1: padding)
+              pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : cl * CELL_CLUSTER + (a & 7), T(0));
+          }
+          stg[a] = pj;
+        }
+        unsafe = PBC == 1 && __any_sync(FULL, unsafe);
+        __syncwarp();
+
+        // one pair: energy, i side in registers, j side (SYM) in the shared accumulators
+        // (ShortestDistance also gets the displacement in double, `ex`: with beta = 100 the weight
+        // moves by 1e-5 when r moves by 1e-7 r, so neither the three roundings of an FP32 r^2 nor
+        // the rounding of a staged image x_j - k L can be afforded)
+        auto interact = [&](const T4& pj, T dx, T dy, T dz, bool checked, const double (&ex)[3]) {
+          const int tagj = tag_decode(pj.w);  // (SYM: the accumulator slot)
+          const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+          // padding never passes the shifted-image test (coordinates 1e18); the minimum-image
+          // reduction of the unsafe path can fold it back, so that path checks the tags
+          bool ok = checked ? (tagj >= 0 && tagi >= 0) : true;
+          T w = T(1);
+          if (OVERLAP) {
+            if (((tagi ^ tagj) & TAG_INDEX_MASK) == 0) ok = false;
+            if (tagi & tagj & TAG_BOTH) w = T(0.5);
+          }
+          if (!ok) return;
+          Acc e[NCH];
+          T coef;
+          if constexpr (FAST6) {
+            contacts_rational6(pc, r2, e[0], coef);
+          } else if constexpr (KIND == CVP_PAIR_SOFTMIN) {
+            Fn::eval_d(pc, ex[0], ex[1], ex[2], fc, e, coef);
+          } else {
+            T4 qj;
+            if (PRM) qj = atom_params[tagj & TAG_INDEX_MASK];
+            Fn::eval(pc, r2, qi, qj, fc, e, coef);
+          }
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) en[c] += Acc(w) * e[c];
+          if (GRAD) {
+            coef *= w;
+            const T fx = coef * dx, fy = coef * dy, fz = coef * dz;
+            gx -= fx;
+            gy -= fy;
+            gz -= fz;
+            if (SYM) sym_add3(jacc + tagj * 3, jwrap + tagj, (float)fx, (float)fy, (float)fz, sym_scale);
+          }
+        };
+
+        // exact displacement of staged atom `slot` from the lane's atom: stored coordinates and the
+        // image count of its cluster, in double (only instantiated for ShortestDistance)
+        auto exact_displacement = [&](int slot, double (&ex)[3]) {
+          const uint32_t ent = lst[bi + (slot >> 3) * nb];
+          const T4 raw = jsm[(int)(ent & 0xffu) * CELL_CLUSTER + (slot & 7)];
+          const uint32_t kx = (ent >> 8) & 3u, ky = (ent >> 10) & 3u, kz = (ent >> 12) & 3u;
+          ex[0] = (double)raw.x - (double)pi.x - (kx == 1u ? (double)bx.ax : (kx == 2u ? -(double)bx.ax : 0.0));
+          ex[1] = (double)raw.y - (double)pi.y - (ky == 1u ? (double)bx.by : (ky == 2u ? -(double)bx.by : 0.0));
+          ex[2] = (double)raw.z - (double)pi.z - (kz == 1u ? (double)bx.cz : (kz == 2u ? -(double)bx.cz : 0.0));
+        };
+
+        if (unsafe) {
+          // some (tile, cluster) pair of the batch is too wide for a single shift (box barely larger
+          // than twice the cutoff): per-pair minimum image, straight loop, compact code
+          for (int slot = 0; slot < take * CELL_CLUSTER; ++slot) {
+            const T4 pj = stg[slot];
+            T dx = pj.x - pr.x, dy = pj.y - pr.y, dz = pj.z - pr.z;
+            pair_min_image<PBC>(dx, dy, dz, bx);
+            if (fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2) {
+              double ex[3] = {(double)dx, (double)dy, (double)dz};
+              if constexpr (KIND == CVP_PAIR_SOFTMIN && PBC == 1) {
+                exact_displacement(slot, ex);
+                ex[0] -= (double)bx.ax * rint(ex[0] / (double)bx.ax);
+                ex[1] -= (double)bx.by * rint(ex[1] / (double)bx.by);
+                ex[2] -= (double)bx.cz * rint(ex[2] / (double)bx.cz);
+              }
+              interact(pj, dx, dy, dz, true, ex);
+            }
+          }
+        } else {
+          // phase 1: bit positions are compile-time constants
+          uint32_t hits[NW];
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            uint32_t m = 0u;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+              const T4 pj = stg[w * 32 + u];
+              const T dx = pj.x - pr.x, dy = pj.y - pr.y, dz = pj.z - pr.z;
+              if (fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2) m |= 1u << u;
+            }
+            hits[w] = m;
+          }
+          int mine = 0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) mine += __popc(hits[w]);
+          const int rounds = __reduce_max_sync(FULL, mine);
+          // phase 2: every lane walks its own hit bits through a working copy `cur` of one mask
+          // word; the next non-empty word is fetched (select chain, no dynamic register indexing)
+          // only when `cur` runs out.  Lanes start at different words, so that neighbouring i atoms
+          // (similar hit lists) do not reach the same j accumulator in the same instruction.
+          static_assert((NW & (NW - 1)) == 0, "NW must be a power of two");
+          int wsel = lane & (NW - 1);
+          uint32_t cur = 0u;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            if (wsel == w) cur = hits[w];
+          }
+          for (int it = 0; it < rounds; ++it) {
+            if (it < mine) {
+              while (cur == 0u) {
+                wsel = (wsel + 1) & (NW - 1);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                  if (wsel == w) cur = hits[w];
+                }
+              }
+              const int k = wsel * 32 + __ffs(cur) - 1;
+              cur &= cur - 1u;
+              const T4 pj = stg[k];
+              double ex[3] = {0.0, 0.0, 0.0};
+              if constexpr (KIND == CVP_PAIR_SOFTMIN) exact_displacement(k, ex);
+              interact(pj, pj.x - pr.x, pj.y - pr.y, pj.z - pr.z, false, ex);
+            }
+          }
+        }
+        __syncwarp();  // the staging buffer is rewritten by the next batch
+      }
       if (GRAD) {
         T4 g;
         g.x = gx;
@@ -642,12 +728,13 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
       // belongs to exactly one chunk, and the passes come in a fixed order)
       __syncthreads();
       T4* jg = jgrad + b * nj_pad + j0;
-      const T inv_scale = T(1) / T(sym_scale);
+      const float inv_scale = 1.0f / sym_scale;
       for (int a = tid; a < jcount; a += CELL_SWEEP_THREADS) {
+        const int wraps = jwrap[a];
         T4 g;
-        g.x = T(jacc[3 * a]) * inv_scale;
-        g.y = T(jacc[3 * a + 1]) * inv_scale;
-        g.z = T(jacc[3 * a + 2]) * inv_scale;
+        g.x = T(sym_value(jacc[3 * a], wraps, 0, inv_scale));
+        g.y = T(sym_value(jacc[3 * a + 1], wraps, 1, inv_scale));
+        g.z = T(sym_value(jacc[3 * a + 2], wraps, 2, inv_scale));
         g.w = T(0);
         if (tile_first > 0) {
           const T4 old = jg[a];
@@ -657,6 +744,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         }
         jg[a] = g;
         jacc[3 * a] = jacc[3 * a + 1] = jacc[3 * a + 2] = 0;
+        jwrap[a] = SYM_WRAP_INIT;
       }
       __syncthreads();
     }

@@ -185,9 +185,19 @@ struct PairFn<T, CVP_PAIR_SOFTMIN> {
   using Acc = double;
   static constexpr int NCH = 2;
   static constexpr bool HAS_PARAMS = false;
+  // With beta = 100 the weight changes by 1e-5 when r changes by 1e-7 r: the squared distance is
+  // formed in double from the (exact) coordinate differences -- three FP32 roundings in r^2 alone
+  // would use up the whole FP32-mode error budget.
+  __device__ static __forceinline__ void eval_d(const PairConsts<T>& pc, double x, double y, double z,
+                                                const double* c, double (&e)[2], T& coef) {
+    eval_r(pc, sqrt(x * x + y * y + z * z), c, e, coef);
+  }
   __device__ static __forceinline__ void eval(const PairConsts<T>& pc, T r2, const T4&, const T4&,
                                               const double* c, double (&e)[2], T& coef) {
-    double r = sqrt((double)r2);
+    eval_r(pc, sqrt((double)r2), c, e, coef);
+  }
+  __device__ static __forceinline__ void eval_r(const PairConsts<T>& pc, double r, const double* c,
+                                                double (&e)[2], T& coef) {
     double w = exp(pc.neg_beta_over_rc * r);
     e[0] = r * w;
     e[1] = w;

@@ -153,7 +153,19 @@ __global__ void __launch_bounds__(PAIR_THREADS)
           }
           Acc e[NCH];
           T coef;
-          Fn::eval(pc, r2, prmi[k], qj, fc, e, coef);
+          if constexpr (KIND == CVP_PAIR_SOFTMIN) {
+            // displacement in double from the stored coordinates (see PairFn<SOFTMIN>)
+            double ex = (double)pj.x - (double)xi[k], ey = (double)pj.y - (double)yi[k],
+                   ez = (double)pj.z - (double)zi[k];
+            if (PBC != 0) {
+              Box<double> bd;
+              bd.ax = bx.ax; bd.bx = bx.bx; bd.by = bx.by; bd.cx = bx.cx; bd.cy = bx.cy; bd.cz = bx.cz;
+              bd.inv_ax = 1.0 / bd.ax; bd.inv_by = 1.0 / bd.by; bd.inv_cz = 1.0 / bd.cz;
+              min_image<PBC>(ex, ey, ez, bd);
+            }
+            Fn::eval_d(pc, ex, ey, ez, fc, e, coef);
+          } else
+            Fn::eval(pc, r2, prmi[k], qj, fc, e, coef);
 #pragma unroll
           for (int c = 0; c < NCH; ++c) en[k][c] += Acc(w) * e[c];
           if (GRAD) {
@@ -413,6 +425,15 @@ struct PairSumCV : cvp_cv {
     bytes += sizeof(double) + 2 * sizeof(double) + 0 * real;       // excluded energy, frame coef
     return bytes;
   }
+  int last_path = -1;      // statistic "last_path": 0 all pairs, 1 cells (two sweeps), 2 cells (symmetric)
+  int get_stat(const char* name, double* out) override {
+    if (std::string(name) == "last_path") {
+      out[0] = last_path;
+      out[1] = 0;
+      return CVP_OK;
+    }
+    return cvp_cv::get_stat(name, out);
+  }
   int set_option(const char* name, int value) override {
     const std::string key(name);
     if (key == "cells") {
@@ -484,9 +505,10 @@ struct PairSumCV : cvp_cv {
     }
     return worst * 1.01;
   }
-  // Decides whether run_cells may use the symmetric sweep; picks the number of passes over the i
-  // tiles and the fixed-point scale (a power of two) such that
-  //   scale * max|dE/dr| * (i atoms per pass) < 2^31   and   scale * max|dE/dr| < 2^22.
+  // Decides whether run_cells may use the symmetric sweep and picks the fixed-point scale, a power of
+  // two such that one contribution fits comfortably (scale * max|dE/dr| < 2^30) and the wrap counters
+  // of pair_cells.cuh cannot leave their 10-bit fields (scale * max|dE/dr| * n_i < 500 * 2^32); the
+  // sum itself may wrap, that is what the counters are for.  One pass over the i tiles.
   template <typename T, int KIND, bool OVERLAP>
   bool sym_plan(bool need_grad, int nsplit, int ni_pad, float* scale, int* passes) const {
     if (!std::is_same<T, float>::value || KIND != CVP_PAIR_CONTACTS || OVERLAP) return false;
@@ -495,18 +517,18 @@ struct PairSumCV : cvp_cv {
       return false;
     const double slope = contacts6_max_slope();
     if (!(slope > 0)) return false;
-    for (int p = 1; p <= 8; p *= 2) {
-      const double per_pass = (double)cell_round_up(cell_round_up(ni_pad, CELL_TILE) / CELL_TILE, p) /
-                              p * CELL_TILE;
-      const double limit = std::min(2147483648.0 / (slope * per_pass), 4194304.0 / slope);
-      const int exponent = (int)std::floor(std::log2(limit * 0.999));
-      if (exponent >= 18 || (p == 8 && exponent >= 16)) {
-        *scale = (float)std::ldexp(1.0, std::min(exponent, 24));
-        *passes = p;
-        return true;
-      }
-    }
-    return false;
+#if SYM_VARIANT == 1 || SYM_VARIANT == 3
+    const double single = 4194304.0 / slope;  // magic-number conversion: |v * scale| < 2^22
+#else
+    const double single = 1073741824.0 / slope;
+#endif
+    const double limit = std::min({67108864.0, single,
+                                   500.0 * 4294967296.0 / (slope * cell_round_up(ni_pad, CELL_TILE))});
+    const int exponent = (int)std::floor(std::log2(limit * 0.999));
+    if (exponent < 16) return false;
+    *scale = (float)std::ldexp(1.0, exponent);
+    *passes = 1;
+    return true;
   }
 
   // ---- cell-sorted fast path (pair_cells.cuh) ----
@@ -581,6 +603,7 @@ struct PairSumCV : cvp_cv {
     float sym_scale = 0.f;
     int sym_passes = 1;
     const bool sym = sym_plan<T, KIND, OVERLAP>(need_grad, nsplit, n1p, &sym_scale, &sym_passes);
+    last_path = sym ? 2 : 1;
     auto sweep = [&](bool first, bool with_grad, const Acc* coef, double* energy) -> int {
       const T4* ip = first ? s1 : s2;
       const T4* jp = first ? s2 : s1;
@@ -662,6 +685,7 @@ struct PairSumCV : cvp_cv {
   template <typename T, int KIND, int PBC, bool OVERLAP>
   int run_impl(const EvalArgs& a, void* ws) {
     if (cells_eligible(PBC)) return run_cells<T, KIND, PBC, OVERLAP>(a, ws);
+    last_path = 0;
     using T4 = typename Vec4<T>::type;
     constexpr int NCH = PairFn<T, KIND>::NCH;
     const int which = std::is_same<T, float>::value ? 0 : 1;

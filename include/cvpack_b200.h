@@ -322,11 +322,15 @@ int cvp_set_option(cvp_cv* cv, const char* name, int value);
  * since the last query (CUDA events on the launching stream; needs option "time_kernels" = 1),
  * out[1] = number of launches.  Kernel names: "sweep" (pair sums), "rmsd_sums", "rmsd_gradient",
  * "rmsd_fused", "rmsd_blocks", "rmsd_multi_cov", "rmsd_multi_gradient", "gyration_sums",
- * "gyration_gradient", "gyration_fused".                                                        */
+ * "gyration_gradient", "gyration_fused".  Pair sums also answer "last_path": out[0] = 0 (all pairs),
+ * 1 (cell-sorted, two sweeps) or 2 (cell-sorted, one symmetric sweep) for the latest evaluation.  */
 int cvp_get_stat(cvp_cv* cv, const char* name, double* out);
 /* Sustained FP32 FMA throughput of `device` in TFLOP/s measured by a register-resident FFMA loop
  * (the FP32 roofline denominator of the pair kernels).                                           */
 int cvp_measure_fp32_peak(int device, double* tflops);
+/* Same for the FP64 pipe (DFMA): the roofline denominator of the double-precision contractions
+ * behind PathInRMSDSpace.                                                                        */
+int cvp_measure_fp64_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -51,8 +51,11 @@ def use_all_threads() -> int:
 
 
 def contacts_batch(x, group1, group2, exclusions=(), box=None, r0=0.3, rc=0.6, rs=0.45,
-                   step_kind=0, step_n=6, reference=1.0, need_grad=True):
-    """NumberOfContacts of every frame of ``x`` [B, N, 3]; returns (value [B], grad [B, N, 3])."""
+                   step_kind=0, step_n=6, reference=1.0, need_grad=True, cells=False):
+    """NumberOfContacts of every frame of ``x`` [B, N, 3]; returns (value [B], grad [B, N, 3]).
+
+    ``cells=True`` uses the cell-list variant (the neighbour-list analogue of OpenMM's CPU platform)
+    and raises ``ValueError`` if the geometry is not supported (triclinic, box < 3 cutoffs)."""
     x = _f64(x)
     num_frames, num_atoms, _ = x.shape
     g1, g2 = _i32(sorted(set(map(int, group1)))), _i32(sorted(set(map(int, group2))))
@@ -72,13 +75,17 @@ def contacts_batch(x, group1, group2, exclusions=(), box=None, r0=0.3, rc=0.6, r
         box = box.reshape(-1)
     value = np.empty(num_frames)
     grad = np.empty_like(x) if need_grad else None
-    load().oracle_contacts_batch(
+    function = load().oracle_contacts_cells_batch if cells else load().oracle_contacts_batch
+    function.restype = C.c_int if cells else None
+    status = function(
         _p(x, _f64p), C.c_int64(num_frames), C.c_int(num_atoms), _p(g1, _i32p), C.c_int(len(g1)),
         _p(g2, _i32p), C.c_int(len(g2)), _p(offsets, _i32p), _p(partners, _i32p), _p(box, _f64p),
         C.c_int(per_frame), C.c_double(r0), C.c_double(rc), C.c_double(-1.0 if rs is None else rs),
         C.c_int(step_kind), C.c_int(step_n), C.c_double(reference), _p(value, _f64p),
         _p(grad, _f64p),
     )
+    if cells and status != 0:
+        raise ValueError("cell-list oracle: unsupported geometry (triclinic box or box < 3 cutoffs)")
     return value, grad
 
 

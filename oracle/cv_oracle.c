@@ -59,7 +59,14 @@ static void step_function(int kind, int n, double x, double* s, double* ds) {
     *ds = 0.0;
     return;
   }
-  double xn1 = pow(x, n - 1);
+  double xn1 = 1.0; /* x^(n-1) by repeated squaring (pow() dominated the in-range pair cost) */
+  {
+    double base = x;
+    for (int e = n - 1; e > 0; e >>= 1) {
+      if (e & 1) xn1 *= base;
+      base *= base;
+    }
+  }
   double inv = 1.0 / (1.0 + xn1 * x);
   *s = inv;
   *ds = -n * xn1 * inv * inv;
@@ -257,4 +264,181 @@ void oracle_gyration_batch(const double* x, int64_t num_frames, int num_atoms,
       for (int k = 0; k < 3; ++k)
         gf[3 * group[i] + k] = factor * (xf[3 * group[i] + k] - c[k] - weights[i] * s[k]);
   }
+}
+
+/*
+ * NumberOfContacts with a cell list -- the CPU analogue of what OpenMM's *CPU* platform does for a
+ * CustomNonbondedForce with a cutoff (a neighbour list instead of the Reference platform's loop over
+ * all |g1| x |g2| pairs).  Same pair set and arithmetic as oracle_contacts_batch (verified against
+ * it in tests/test_oracle.py); rectangular periodic box or no box.  The group-2 atoms of a frame
+ * are binned in cells of edge >= rc; every group-1 atom visits the 27 surrounding cells.  This is
+ * the fair CPU arm of bench.py: O(N) per frame, OpenMP over frames.
+ * Returns 0, or -1 if the geometry is not supported (triclinic box, fewer than 3 cells per axis
+ * in a periodic box: callers fall back to oracle_contacts_batch).
+ */
+int oracle_contacts_cells_batch(const double* x, int64_t num_frames, int num_atoms,
+                                const int32_t* g1, int n1, const int32_t* g2, int n2,
+                                const int32_t* ex_offsets, const int32_t* ex_partners,
+                                const double* box, int box_per_frame, double r0, double rc,
+                                double rs, int step_kind, int step_n, double reference,
+                                double* value, double* grad) {
+  if (box) {
+    const int64_t boxes = box_per_frame ? num_frames : 1;
+    for (int64_t b = 0; b < boxes; ++b) {
+      const double* bx = box + 9 * b;
+      if (bx[1] != 0 || bx[2] != 0 || bx[3] != 0 || bx[5] != 0 || bx[6] != 0 || bx[7] != 0) return -1;
+      if (bx[0] < 3 * rc || bx[4] < 3 * rc || bx[8] < 3 * rc) return -1;
+    }
+  }
+  char* in1 = calloc(num_atoms, 1);
+  char* in2 = calloc(num_atoms, 1);
+  for (int i = 0; i < n1; ++i) in1[g1[i]] = 1;
+  for (int j = 0; j < n2; ++j) in2[g2[j]] = 1;
+#pragma omp parallel
+  {
+    int* cell_of = malloc(sizeof(int) * (size_t)n2);
+    int* order = malloc(sizeof(int) * (size_t)n2);
+    double* wrapped = malloc(sizeof(double) * 3 * (size_t)n2);
+    int* start = NULL;
+    int start_cap = 0;
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t b = 0; b < num_frames; ++b) {
+      const double* xf = x + b * (int64_t)num_atoms * 3;
+      const double* bx = box ? box + (box_per_frame ? b * 9 : 0) : NULL;
+      double* gf = grad ? grad + b * (int64_t)num_atoms * 3 : NULL;
+      if (gf) memset(gf, 0, sizeof(double) * 3 * num_atoms);
+      /* grid: the periodic box, or the bounding box of group 2 */
+      double lo[3], len[3];
+      if (bx) {
+        lo[0] = lo[1] = lo[2] = 0.0;
+        len[0] = bx[0]; len[1] = bx[4]; len[2] = bx[8];
+      } else {
+        for (int k = 0; k < 3; ++k) { lo[k] = 1e300; len[k] = -1e300; }
+        for (int c = 0; c < n2; ++c)
+          for (int k = 0; k < 3; ++k) {
+            const double v = xf[3 * g2[c] + k];
+            if (v < lo[k]) lo[k] = v;
+            if (v > len[k]) len[k] = v;
+          }
+        for (int k = 0; k < 3; ++k) len[k] = fmax(len[k] - lo[k], 1e-9) * (1.0 + 1e-12) + 1e-12;
+      }
+      /* cells of edge >= rc/m, neighbours within +-m cells (m = 2 when the box allows it: the
+         candidate volume drops from 27 (rc)^3-cells to the cells that can reach the cutoff sphere) */
+      int dims[3], m = 2;
+      for (int k = 0; k < 3; ++k)
+        if (bx && (int)floor(len[k] / (0.5 * rc)) < 5) m = 1;
+      for (int k = 0; k < 3; ++k) {
+        dims[k] = (int)floor(len[k] / (rc / m));
+        if (dims[k] < 1) dims[k] = 1;
+        if (dims[k] > 128) dims[k] = 128;
+      }
+      double edge[3];
+      for (int k = 0; k < 3; ++k) edge[k] = len[k] / dims[k];
+      const int ncells = dims[0] * dims[1] * dims[2];
+      if (ncells + 1 > start_cap) {
+        free(start);
+        start_cap = ncells + 1;
+        start = malloc(sizeof(int) * (size_t)start_cap);
+      }
+      memset(start, 0, sizeof(int) * (size_t)(ncells + 1));
+      for (int c = 0; c < n2; ++c) {
+        int cc[3];
+        for (int k = 0; k < 3; ++k) {
+          double v = xf[3 * g2[c] + k];
+          if (bx) v -= len[k] * floor(v / len[k]);
+          wrapped[3 * c + k] = v;
+          int q = (int)((v - lo[k]) / len[k] * dims[k]);
+          cc[k] = q < 0 ? 0 : (q >= dims[k] ? dims[k] - 1 : q);
+        }
+        cell_of[c] = (cc[2] * dims[1] + cc[1]) * dims[0] + cc[0];
+        start[cell_of[c] + 1]++;
+      }
+      for (int c = 0; c < ncells; ++c) start[c + 1] += start[c];
+      /* stable counting sort: inside a cell the group order is kept, so sums have a fixed order */
+      {
+        int* fill = malloc(sizeof(int) * (size_t)ncells);
+        memcpy(fill, start, sizeof(int) * (size_t)ncells);
+        for (int c = 0; c < n2; ++c) order[fill[cell_of[c]]++] = c;
+        free(fill);
+      }
+      double total = 0.0;
+      for (int a = 0; a < n1; ++a) {
+        const int i = g1[a];
+        double xi[3];
+        int ci[3];
+        for (int k = 0; k < 3; ++k) {
+          double v = xf[3 * i + k];
+          if (bx) v -= len[k] * floor(v / len[k]);
+          xi[k] = v;
+          ci[k] = (int)floor((v - lo[k]) / len[k] * dims[k]);
+          /* no box: an atom outside the bounding box of group 2 is clamped to the layer just
+             outside it -- it then sees the border cells (extra candidates fail the distance test) */
+          if (!bx) ci[k] = ci[k] < -m ? -m : (ci[k] > dims[k] + m - 1 ? dims[k] + m - 1 : ci[k]);
+        }
+        for (int dz = -m; dz <= m; ++dz)
+          for (int dy = -m; dy <= m; ++dy)
+            for (int dx = -m; dx <= m; ++dx) {
+              int cc[3] = {ci[0] + dx, ci[1] + dy, ci[2] + dz};
+              /* cells that cannot reach the cutoff sphere of any atom of the home cell */
+              const double gx = (abs(dx) > 1 ? abs(dx) - 1 : 0) * edge[0];
+              const double gy = (abs(dy) > 1 ? abs(dy) - 1 : 0) * edge[1];
+              const double gz = (abs(dz) > 1 ? abs(dz) - 1 : 0) * edge[2];
+              if (gx * gx + gy * gy + gz * gz >= rc * rc) continue;
+              int skip = 0;
+              for (int k = 0; k < 3; ++k) {
+                if (bx) cc[k] = (cc[k] % dims[k] + dims[k]) % dims[k];  /* >= 2m+1 cells: all distinct */
+                else if (cc[k] < 0 || cc[k] >= dims[k]) skip = 1;
+              }
+              if (skip) continue;
+              const int cell = (cc[2] * dims[1] + cc[1]) * dims[0] + cc[0];
+              for (int s = start[cell]; s < start[cell + 1]; ++s) {
+                const int c = order[s];
+                const int j = g2[c];
+                if (i == j) continue;
+                if (in1[j] && in2[i] && j < i) continue;
+                if (ex_offsets) {
+                  int excluded = 0;
+                  for (int e = ex_offsets[i]; e < ex_offsets[i + 1]; ++e)
+                    if (ex_partners[e] == j) { excluded = 1; break; }
+                  if (excluded) continue;
+                }
+                double d[3];
+                for (int k = 0; k < 3; ++k) {
+                  d[k] = wrapped[3 * c + k] - xi[k];
+                  if (bx) d[k] -= len[k] * floor(d[k] / len[k] + 0.5);
+                }
+                const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                if (r2 >= rc * rc) continue;
+                const double r = sqrt(r2);
+                double sv, ds;
+                step_function(step_kind, step_n, r / r0, &sv, &ds);
+                double de = ds / r0;
+                if (rs > 0.0 && r > rs) {
+                  const double t = (r - rs) / (rc - rs);
+                  const double sw = 1.0 + t * t * t * (-10.0 + t * (15.0 - 6.0 * t));
+                  const double dsw = t * t * (-30.0 + t * (60.0 - 30.0 * t)) / (rc - rs);
+                  de = de * sw + sv * dsw;
+                  sv *= sw;
+                }
+                total += sv;
+                if (gf && r > 0.0) {
+                  const double f = de / r / reference;
+                  for (int k = 0; k < 3; ++k) {
+                    gf[3 * j + k] += f * d[k];
+                    gf[3 * i + k] -= f * d[k];
+                  }
+                }
+              }
+            }
+      }
+      value[b] = total / reference;
+    }
+    free(cell_of);
+    free(order);
+    free(wrapped);
+    free(start);
+  }
+  free(in1);
+  free(in2);
+  return 0;
 }

@@ -339,3 +339,46 @@ def test_rmsd_of_nearly_identical_frames(frames):
     big = ref_value > 1e-4  # the gradient direction of a vanishing RMSD is ill-conditioned in FP32
     err = np.abs(g[big] - ref_grad[big]).max(axis=(1, 2)) / np.abs(ref_grad[big]).max(axis=(1, 2))
     assert err.max() <= 2e-3
+
+
+def test_symmetric_sweep_dilute_frames():
+    """Frames whose gradients are tiny: every group-1 atom has one partner of group 2 at 0.12-0.25 nm
+    (far inside r0 = 0.6 nm, where dS/dr ~ x^5 is 1e-3 .. 0.13) and nothing else within the cutoff.
+    The j side of the symmetric sweep is accumulated in fixed point: its quantum must be negligible
+    against *these* gradients too -- the error is measured relative to the largest component of each
+    frame, like everywhere else -- while the sums of a dense frame in the same batch must survive the
+    wrap of the 32-bit accumulators."""
+    rng = np.random.default_rng(39)
+    m, spacing = 6, 1.45
+    sites = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3) * spacing
+    n1 = len(sites)
+    box, frames, n = m * spacing, 150, 2 * len(sites)
+    x = np.empty((frames, n, 3))
+    x[:, :n1] = sites[None] + rng.uniform(0, 0.05, size=(frames, n1, 3))
+    offset = rng.normal(size=(frames, n1, 3))
+    offset *= rng.uniform(0.12, 0.25, size=(frames, n1, 1)) / np.linalg.norm(offset, axis=2, keepdims=True)
+    x[:, n1:] = x[:, :n1] + offset
+    x[7] = rng.uniform(0.0, 1.5, size=(n, 3))   # one dense frame: a hundred contacts per atom
+    system = unit_system(n)
+    cv = cvpack.NumberOfContacts(range(0, n1), range(n1, n), plain_nonbonded(n, True), thresholdDistance=0.6)
+    cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, [box] * 3)
+    native = ctx._native_cv(cv)  # pylint: disable=protected-access
+    value, grad = cv.getValueAndGradient(ctx)
+    assert int(native.stat("last_path")) == 2, "expected the symmetric sweep"
+    stored = ctx.getPositions().double().cpu().numpy()
+    ref_value, ref_grad = c_oracle.contacts_batch(
+        stored, range(0, n1), range(n1, n), (), np.diag([box] * 3), r0=0.6, rc=1.2, rs=0.9, cells=True,
+    )
+    v, g = value._value.double().cpu().numpy(), grad.double().cpu().numpy()
+    largest = np.abs(ref_grad).reshape(frames, -1).max(axis=1)
+    dilute = np.delete(np.arange(frames), 7)
+    assert 0 < largest[dilute].max() < 0.2, largest[dilute].max()
+    assert largest[7] > 10.0
+    for b in range(frames):
+        assert abs(v[b] - ref_value[b]) <= 1e-5 * abs(ref_value[b]), (b, v[b], ref_value[b])
+        err = np.abs(g[b] - ref_grad[b]).max() / largest[b]
+        assert err <= 1e-5, f"frame {b}: gradient error {err:.2e} of the largest component {largest[b]:.3g}"
+        assert np.array_equal(g[b] != 0, ref_grad[b] != 0)
+    # Newton's third law holds to the quantum of the accumulators, frame by frame
+    assert np.abs(g[dilute].sum(axis=1)).max() <= 1e-5 * largest[dilute].max() * np.sqrt(n)

@@ -313,3 +313,31 @@ def test_c_oracle_matches_numpy():
         ref_value, ref_grad = o.radius_of_gyration(x[b], group, weights)
         assert gvalue[b] == pytest.approx(ref_value, rel=1e-12)
         assert np.abs(ggrad[b] - ref_grad).max() < 1e-12
+
+
+def test_c_oracle_cell_list_matches_all_pairs():
+    """The cell-list CPU arm of bench.py (neighbour-list analogue of OpenMM's CPU platform) visits the
+    same pairs as the all-pairs Reference-platform loop: same values, gradients to summation order."""
+    rng = np.random.default_rng(12)
+    n = 900
+    x = rng.uniform(-0.3, 2.9, size=(4, n, 3))  # some atoms outside the box: wrapped
+    g1, g2 = list(range(0, 500)), list(range(400, 900))
+    ex = [(0, 450), (410, 420), (5, 700), (499, 500)]
+    boxes = [None, np.diag([2.6, 2.7, 2.8]), np.stack([np.diag([2.6 + 0.1 * k] * 3) for k in range(4)])]
+    for box in boxes:
+        for rs in (0.6, None):
+            ref_value, ref_grad = c_oracle.contacts_batch(x, g1, g2, ex, box, r0=0.4, rc=0.8, rs=rs)
+            value, grad = c_oracle.contacts_batch(x, g1, g2, ex, box, r0=0.4, rc=0.8, rs=rs, cells=True)
+            assert np.allclose(value, ref_value, rtol=1e-13, atol=0)
+            assert np.abs(grad - ref_grad).max() <= 1e-12 * np.abs(ref_grad).max()
+            assert np.array_equal(grad != 0, ref_grad != 0)
+    # group 1 far from the bounding box of group 2 (no box): border cells still reached
+    y = x.copy()
+    y[:, :400] += np.array([3.3, 0.0, 0.0])
+    ref_value, ref_grad = c_oracle.contacts_batch(y, g1, g2, ex, None, r0=0.4, rc=0.8)
+    value, grad = c_oracle.contacts_batch(y, g1, g2, ex, None, r0=0.4, rc=0.8, cells=True)
+    assert np.allclose(value, ref_value, rtol=1e-13) and np.abs(grad - ref_grad).max() <= 1e-12
+    with pytest.raises(ValueError):
+        c_oracle.contacts_batch(x, g1, g2, ex, TRICLINIC, cells=True)
+    with pytest.raises(ValueError):
+        c_oracle.contacts_batch(x, g1, g2, ex, np.diag([2.0, 2.0, 2.0]), r0=0.4, rc=0.8, cells=True)
