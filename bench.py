@@ -49,6 +49,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+RECORD: list = []  # the JSON line, printed by main() once stdout is ours again
 HEADLINE = dict(frames=4096, atoms=20000, box=5.844, r0=0.6, cpu_sample_frames=32)
 TOLERANCE = 1e-5  # north_star: FP32 mode within 1e-5 relative of the Reference-platform result
 
@@ -259,7 +260,7 @@ def run_reference(args) -> None:
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    RECORD.append(json.dumps(line))
 
 
 def headline_cpu_baseline(spec: dict):
@@ -567,6 +568,7 @@ def run_scale_extras(device, rank, world, steps) -> dict:
 
     def timed(fn, reps):
         fn()
+        fn()
         dist.barrier()
         torch.cuda.synchronize()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -615,6 +617,7 @@ def run_scale_extras(device, rank, world, steps) -> dict:
     grads = {k: torch.empty((local, n, 3), device=device) for k in cvs}
     native = ctx._native_cv(cvs["contacts"])  # pylint: disable=protected-access
     active = torch.as_tensor(native.active_atoms().astype(np.int64), device=device)
+    active32 = active.int()
 
     def compute():
         for key, cv_ in cvs.items():
@@ -651,24 +654,38 @@ def run_scale_extras(device, rank, world, steps) -> dict:
     if hasattr(distributed, "PeerGather"):
         try:
             peer = distributed.PeerGather(walkers_total, n, torch.float32, device)
-            chunks = 4
-            bounds = [local * k // chunks for k in range(chunks + 1)]
+            half = local // 2
             side = torch.cuda.Stream(device=device)
 
             def peer_run(compact: bool, overlap: bool):
+                """overlap: the contact CV is evaluated in two slabs; slab 1 travels while slab 2 is
+                computed, slab 2 while the second CV (CompositeRMSD) is computed."""
+                atoms = active32 if compact else None
+
+                def evaluate(key, lo, hi):
+                    ctx._run(cvs[key], True, positions=x[lo:hi], out=(values[key][lo:hi], grads[key][lo:hi]))  # pylint: disable=protected-access
+
+                def push_after(lo, hi):
+                    done = torch.cuda.Event()
+                    done.record(torch.cuda.current_stream(device))
+                    side.wait_event(done)
+                    with torch.cuda.stream(side):
+                        peer.push(grads["contacts"][lo:hi], begin + lo, atoms)
+
                 def run():
-                    main = torch.cuda.current_stream(device)
-                    for k in range(chunks if overlap else 1):
-                        lo, hi = (bounds[k], bounds[k + 1]) if overlap else (0, local)
-                        for key, cv_ in cvs.items():
-                            ctx._run(cv_, True, positions=x[lo:hi], out=(values[key][lo:hi], grads[key][lo:hi]))  # pylint: disable=protected-access
-                        done = torch.cuda.Event()
-                        done.record(main)
-                        side.wait_event(done)
-                        with torch.cuda.stream(side):
-                            peer.push(grads["contacts"][lo:hi], begin + lo, active if compact else None)
-                    peer.finish(side)
-                    main.wait_stream(side)
+                    if overlap:
+                        evaluate("contacts", 0, half)
+                        push_after(0, half)
+                        evaluate("contacts", half, local)
+                        push_after(half, local)
+                        evaluate("composite", 0, local)
+                    else:
+                        evaluate("contacts", 0, local)
+                        evaluate("composite", 0, local)
+                        push_after(0, local)
+                    result = peer.finish(side)
+                    torch.cuda.current_stream(device).wait_stream(side)
+                    return result
                 return run
 
             for compact in (False, True):
@@ -677,10 +694,13 @@ def run_scale_extras(device, rank, world, steps) -> dict:
                     record[key] = gather_record(timed(peer_run(compact, overlap), steps),
                                                 compact_bytes if compact else dense_bytes)
             # the pushed buffer must equal the NCCL gather
-            peer_run(False, False)()
+            result = peer_run(False, False)()
             torch.cuda.synchronize()
             reference = distributed.all_gather_gradients(grads["contacts"], walkers_total)
-            record["peer_equals_nccl"] = bool(torch.equal(peer.tensor(), reference))
+            record["peer_equals_nccl"] = bool(torch.equal(result, reference))
+            record["peer_timed_out"] = peer.timed_out()
+            del reference
+            dist.barrier()
             peer.close()
         except Exception as error:  # pylint: disable=broad-except
             record["peer_error"] = f"{type(error).__name__}: {error}"
@@ -896,7 +916,7 @@ def run_ours(args) -> None:
         line["extra"] = extra
     if scale_extra is not None:
         line["scale_extra"] = scale_extra
-    print(json.dumps(line), flush=True)
+    RECORD.append(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
     failed = [r["name"] for r in (extra or []) if r.get("parity") and not r["parity"]["ok"]]
@@ -919,10 +939,22 @@ def main() -> None:
     parser.add_argument("--extras", default="all", help="comma-separated subset of the extra records "
                         "(rmsd,rg,path,helix_rmsd,helix_torsion,walkers_contacts,walkers_composite_rmsd,contacts_fp64)")
     args = parser.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line (the JSON record): whatever libraries print there (NCCL's
+    # version banner, torchrun notices) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        if RECORD:
+            print(RECORD[-1], flush=True)
 
 
 if __name__ == "__main__":

@@ -198,6 +198,15 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     "cvp_path_cv_combine": (C.c_int, [C.POINTER(PathCVDesc), C.c_int, _vp, C.c_int64, _vp, _vp, _vp]),
     "cvp_expr_eval": (C.c_int, [C.POINTER(ExprProgram), C.c_int, _vp, C.c_int64, _vp, _vp, _vp]),
     "cvp_axpy_frames": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int, _vp]),
+    "cvp_peer_buffer_create": (C.c_int, [C.c_int64, C.POINTER(_vp)]),
+    "cvp_peer_buffer_handle": (C.c_int, [_vp, _vp]),
+    "cvp_peer_buffer_open": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "cvp_peer_buffer_local": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
+    "cvp_peer_push": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int32, _vp]),
+    "cvp_peer_signal": (C.c_int, [_vp, _vp]),
+    "cvp_peer_wait": (C.c_int, [_vp, _vp]),
+    "cvp_peer_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "cvp_peer_buffer_destroy": (C.c_int, [_vp]),
     "cvp_last_error": (C.c_char_p, []),
     "cvp_version": (C.c_int, []),
     "cvp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -12,11 +12,13 @@ which is what makes the gather cheap for CVs that touch a small part of a large 
 
 from __future__ import annotations
 
+import ctypes as C
 import typing as t
 
 import torch
 import torch.distributed as dist
 
+from . import _native
 from .batch import shard_frames
 
 
@@ -85,3 +87,121 @@ def all_gather_gradients(
     )
     dense.index_copy_(1, index, gathered)
     return dense
+
+
+class _DevicePointer:  # pylint: disable=too-few-public-methods
+    """Adapter that lets torch alias raw device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape: t.Tuple[int, ...], typestr: str) -> None:
+        self.__cuda_array_interface__ = {
+            "shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+class PeerGather:
+    """
+    All-gather of gradients ``[b_local, N, 3] -> [num_frames, N, 3]`` through the library's own
+    peer-memory collective (``csrc/peer.cu``): every rank owns a gather buffer, maps the others'
+    through CUDA IPC, and :meth:`push` writes a slab of local frames into *every* rank's buffer with
+    one kernel (remote stores over NVLink).  With ``active_atoms`` only those atoms travel and land
+    in place -- compaction, transfer and re-expansion are one pass.  Pushes are ordered on the
+    current stream, so chunks can be pushed while the next chunk is evaluated; :meth:`finish` is a
+    stream-ordered barrier (no host synchronisation).
+
+    One process per GPU on one node; ``group`` is only used to exchange the 64-byte IPC handles.
+    ``depth`` buffers are used in turn (2 lets a step be consumed while the next one is gathered).
+    """
+
+    def __init__(  # pylint: disable=too-many-arguments
+        self, num_frames: int, num_atoms: int, dtype: torch.dtype, device: torch.device,
+        group: t.Optional[t.Any] = None, depth: int = 1,
+    ) -> None:
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("gradients are float32 or float64")
+        self._rank, self._world = _world(group)
+        self._shape = (int(num_frames), int(num_atoms), 3)
+        self._dtype = dtype
+        self._cvp_dtype = _native.CVP_F32 if dtype == torch.float32 else _native.CVP_F64
+        self._device = torch.device(device)
+        self._buffers: t.List[int] = []
+        self._tensors: t.List[torch.Tensor] = []
+        self._turn = 0
+        lib = _native.load()
+        element = 4 if dtype == torch.float32 else 8
+        nbytes = self._shape[0] * self._shape[1] * 3 * element
+        with torch.cuda.device(self._device):
+            for _ in range(max(1, depth)):
+                handle = C.c_void_p()
+                _native.check(lib.cvp_peer_buffer_create(nbytes, C.byref(handle)))
+                self._buffers.append(handle.value)
+                ipc = C.create_string_buffer(64)
+                _native.check(lib.cvp_peer_buffer_handle(handle.value, ipc))
+                handles: t.List[t.Any] = [None] * self._world
+                if self._world > 1:
+                    dist.all_gather_object(handles, ipc.raw, group=group)
+                else:
+                    handles = [ipc.raw]
+                packed = C.create_string_buffer(b"".join(handles), 64 * self._world)
+                _native.check(lib.cvp_peer_buffer_open(handle.value, self._world, self._rank, packed))
+                ptr, size = C.c_void_p(), C.c_int64()
+                _native.check(lib.cvp_peer_buffer_local(handle.value, C.byref(ptr), C.byref(size)))
+                view = torch.as_tensor(
+                    _DevicePointer(ptr.value, self._shape, "<f4" if dtype == torch.float32 else "<f8"),
+                    device=self._device,
+                )
+                self._tensors.append(view)
+        if self._world > 1:
+            dist.barrier(group=group)  # every rank has mapped every buffer before anyone pushes
+
+    def tensor(self) -> torch.Tensor:
+        """The gather buffer of the current turn as a ``[num_frames, N, 3]`` tensor (aliases it)."""
+        return self._tensors[self._turn]
+
+    def push(self, gradient: torch.Tensor, first_frame: int, active_atoms: t.Optional[torch.Tensor] = None) -> None:
+        """Write ``gradient`` ``[b, N, 3]`` (frames ``first_frame ...`` of the batch) into every rank's
+        buffer, on the current stream.  ``active_atoms``: int32 CUDA tensor of the atoms to move."""
+        if gradient.dtype != self._dtype or not gradient.is_cuda or not gradient.is_contiguous():
+            raise ValueError("gradient must be a contiguous CUDA tensor of the buffer's dtype")
+        if tuple(gradient.shape[1:]) != self._shape[1:]:
+            raise ValueError(f"gradient must have shape [b, {self._shape[1]}, 3]")
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        active_ptr, count = None, 0
+        if active_atoms is not None:
+            if active_atoms.dtype != torch.int32 or not active_atoms.is_cuda:
+                raise ValueError("active_atoms must be an int32 CUDA tensor")
+            active_ptr, count = active_atoms.data_ptr(), int(active_atoms.numel())
+        _native.check(
+            _native.load().cvp_peer_push(
+                self._buffers[self._turn], self._cvp_dtype, gradient.data_ptr(), int(first_frame),
+                int(gradient.shape[0]), self._shape[1], active_ptr, count, stream,
+            )
+        )
+
+    def finish(self, stream: t.Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """Stream-ordered barrier: after it (on that stream) the buffer holds every rank's frames.
+        Returns the gathered tensor and moves on to the next buffer of the ring."""
+        cuda_stream = (stream or torch.cuda.current_stream(self._device)).cuda_stream
+        lib = _native.load()
+        _native.check(lib.cvp_peer_signal(self._buffers[self._turn], cuda_stream))
+        _native.check(lib.cvp_peer_wait(self._buffers[self._turn], cuda_stream))
+        gathered = self._tensors[self._turn]
+        self._turn = (self._turn + 1) % len(self._buffers)
+        return gathered
+
+    def timed_out(self) -> bool:
+        """Whether a wait gave up (a rank never signalled); synchronises the device."""
+        flag = C.c_int()
+        result = False
+        for handle in self._buffers:
+            _native.check(_native.load().cvp_peer_status(handle, C.byref(flag)))
+            result = result or bool(flag.value)
+        return result
+
+    def close(self) -> None:
+        """Unmap the peers' buffers and free this rank's (all ranks, after a barrier)."""
+        torch.cuda.synchronize(self._device)
+        self._tensors.clear()
+        lib = _native.load()
+        for handle in self._buffers:
+            lib.cvp_peer_buffer_destroy(handle)
+        self._buffers = []

@@ -307,6 +307,31 @@ int cvp_expr_eval(const cvp_expr_program* program, int dtype, const void* values
 int cvp_axpy_frames(int dtype, const void* coef, const void* x, void* y, int64_t num_frames,
                     int64_t num_atoms, int accumulate, void* stream);
 
+/* ---- gathering gradients across the GPUs of one box (NVLink / NVSwitch peer memory) ------------ */
+/* north_star: "NCCL over NVLink used only to gather CV values and gradients"; SURVEY section 8(b) calls
+ * the entry cvp_allgather.  Values ([B] numbers) are gathered by the host language over NCCL; for
+ * gradients the library has its own collective: every rank owns a gather buffer [B_total][N][3]
+ * exported as a 64-byte CUDA IPC handle, ranks exchange the handles out of band and map each
+ * other's buffers, and cvp_peer_push writes the caller's frames into every rank's buffer with one
+ * kernel (remote stores over NVLink).  With `active` (cvp_active_atoms, device int32) only those
+ * atoms travel and land at their place in the dense buffers.  All calls are ordered on `stream`;
+ * cvp_peer_signal + cvp_peer_wait form a stream-ordered barrier (every rank calls both, the same
+ * number of times): after the wait, the frames pushed by all ranks before their signal are
+ * visible in the local buffer.  The wait gives up after ~4 s (cvp_peer_status reports it).
+ * One process per GPU; the current device at cvp_peer_buffer_create owns the buffer.             */
+typedef struct cvp_peer_buffer cvp_peer_buffer;
+int cvp_peer_buffer_create(int64_t bytes, cvp_peer_buffer** out);
+int cvp_peer_buffer_handle(cvp_peer_buffer* buffer, void* handle64);
+int cvp_peer_buffer_open(cvp_peer_buffer* buffer, int world, int rank, const void* handles /* [world][64] */);
+int cvp_peer_buffer_local(cvp_peer_buffer* buffer, void** ptr, int64_t* bytes);
+int cvp_peer_push(cvp_peer_buffer* buffer, int dtype, const void* src /* [count][N][3] device */,
+                  int64_t first_frame, int64_t num_frames, int64_t num_atoms,
+                  const int32_t* active /* device, or NULL = dense */, int32_t num_active, void* stream);
+int cvp_peer_signal(cvp_peer_buffer* buffer, void* stream);
+int cvp_peer_wait(cvp_peer_buffer* buffer, void* stream);
+int cvp_peer_status(cvp_peer_buffer* buffer, int* timed_out);
+int cvp_peer_buffer_destroy(cvp_peer_buffer* buffer);
+
 /* ---- diagnostics ------------------------------------------------------------------------------- */
 const char* cvp_last_error(void);
 int cvp_version(void);
