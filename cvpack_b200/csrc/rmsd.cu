@@ -750,6 +750,7 @@ struct RmsdCV : cvp_cv {
   // many references over one contiguous atom set (rmsd_multi.cuh)
   bool multi = false;
   int use_multi = 1;  // option "multi"
+  int use_multi_mma = 1;  // option "multi_mma": FP64 tensor-core (DMMA) versions of the multi kernels
   int multi_first = 0, multi_n = 0, multi_sk_max = 1;
   std::vector<float> ref_f32;
   std::vector<int32_t> fast_seg_slice_offsets;
@@ -825,6 +826,10 @@ struct RmsdCV : cvp_cv {
     }
     if (key == "multi") {
       std::swap(use_multi, value);
+      return value;
+    }
+    if (key == "multi_mma") {
+      std::swap(use_multi_mma, value);
       return value;
     }
     if (key == "blocks") {
@@ -926,9 +931,14 @@ struct RmsdCV : cvp_cv {
       const dim3 cov_grid((unsigned)div_up(B, MULTI_TF), (unsigned)div_up(num_groups, MULTI_TG),
                           (unsigned)multi_sk);
       timer.begin("rmsd_multi_cov", st);
-      rmsd_multi_cov_kernel<<<cov_grid, MULTI_THREADS, 0, st>>>(
-          reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
-          static_cast<const double*>(d_ref.ptr), num_groups, B, multi_sk, partials);
+      if (use_multi_mma)
+        rmsd_multi_cov_mma_kernel<<<cov_grid, MULTI_THREADS, 0, st>>>(
+            reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+            static_cast<const double*>(d_ref.ptr), num_groups, B, multi_sk, partials);
+      else
+        rmsd_multi_cov_kernel<<<cov_grid, MULTI_THREADS, 0, st>>>(
+            reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+            static_cast<const double*>(d_ref.ptr), num_groups, B, multi_sk, partials);
       CVP_LAUNCH_CHECK();
       rmsd_multi_moments_kernel<<<(unsigned)div_up(B * multi_sk * 32, 256), 256, 0, st>>>(
           reinterpret_cast<const float*>(pos), N, multi_first, multi_n, num_groups, B, multi_sk,
@@ -948,12 +958,16 @@ struct RmsdCV : cvp_cv {
       if (grad == nullptr) return CVP_OK;
       if (!accumulate && !dense)
         CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
-      const dim3 grad_grid((unsigned)div_up(B, MULTI_TF), (unsigned)div_up(multi_n, MULTI_TA));
+      const dim3 grad_grid((unsigned)div_up(B, MULTI_TF),
+                           (unsigned)div_up(multi_n, use_multi_mma ? MMA_TA : MULTI_TA));
       static bool multi_configured = false;
       if (!multi_configured) {
         CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_gradient_kernel,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)MULTI_GRAD_SMEM));
+        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_gradient_mma_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)MULTI_GRAD_MMA_SMEM));
         multi_configured = true;
       }
       // the slice records are dead after the solve: their memory holds the W = factor * U^T records
@@ -963,10 +977,16 @@ struct RmsdCV : cvp_cv {
           solution, group_factor, B * (int64_t)num_groups, weights);
       CVP_LAUNCH_CHECK();
       timer.begin("rmsd_multi_gradient", st);
-      rmsd_multi_gradient_kernel<<<grad_grid, MULTI_THREADS, MULTI_GRAD_SMEM, st>>>(
-          reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
-          static_cast<const double*>(d_ref.ptr), num_groups, B, weights,
-          seg_centroid, nseg, reinterpret_cast<float*>(grad), accumulate ? 1 : 0);
+      if (use_multi_mma)
+        rmsd_multi_gradient_mma_kernel<<<grad_grid, MULTI_THREADS, MULTI_GRAD_MMA_SMEM, st>>>(
+            reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+            static_cast<const double*>(d_ref.ptr), num_groups, B, weights,
+            seg_centroid, nseg, reinterpret_cast<float*>(grad), accumulate ? 1 : 0);
+      else
+        rmsd_multi_gradient_kernel<<<grad_grid, MULTI_THREADS, MULTI_GRAD_SMEM, st>>>(
+            reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+            static_cast<const double*>(d_ref.ptr), num_groups, B, weights,
+            seg_centroid, nseg, reinterpret_cast<float*>(grad), accumulate ? 1 : 0);
       timer.end(st);
       CVP_LAUNCH_CHECK();
       return CVP_OK;

@@ -373,6 +373,302 @@ __global__ void __launch_bounds__(MULTI_THREADS, 1)
   }
 }
 
+// ---- FP64 tensor-core versions (mma.sync.m8n8k4.f64, DMMA) ----------------------------------------
+// Both contractions above run at 41-51 % of the FP64 pipe: what limits them is shared memory, a
+// 128-bit shared load costs four wavefronts whatever is broadcast (ncu, round 1).  With the tensor
+// core instruction a warp multiplies an 8 x 4 by a 4 x 8 tile (256 DFMA) from ONE double per
+// thread and operand: the operand tiles are stored in shared memory in fragment order (32
+// consecutive doubles per 8 x 4 tile, lane l reads element l: conflict-free LDS.64) and a warp tile
+// of 3 x 6 (covariance) / 3 x 8 (gradient) MMA tiles needs 9 / 11 loads per 18 / 24 instructions.
+//   fragment layouts (PTX ISA, m8n8k4 .f64):  A[row = lane / 4][k = lane % 4],
+//   B[k = lane % 4][col = lane / 4],  C[row = lane / 4][col = 2 (lane % 4) + {0, 1}]
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+constexpr int MMA_KA = 16;  // atoms per stage of the covariance (4 k-steps)
+constexpr int MMA_ROWS = 3 * MULTI_TF;  // 96 = 12 tiles of 8 rows (frame, component)
+
+// covariance: M = (frame, c) 96 rows, N = (group, d) 96 columns, K = atoms.
+// grid = (frame tiles, group tiles, SK); same partial-sum records as rmsd_multi_cov_kernel.
+__global__ void __launch_bounds__(MULTI_THREADS, 2)
+    rmsd_multi_cov_mma_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom, int n,
+                              const double* __restrict__ ref /* [G][n][3], centred */, int num_groups,
+                              int64_t num_frames, int SK, double* __restrict__ partials) {
+  // [buffer][k-step][tile][fragment element]
+  __shared__ __align__(16) double As[2][MMA_KA / 4][MMA_ROWS / 8][32];
+  __shared__ __align__(16) double Bs[2][MMA_KA / 4][MMA_ROWS / 8][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;  // row tiles 3 wm .. 3 wm + 2, column tiles 6 wn .. 6 wn + 5
+  const int64_t f0 = (int64_t)blockIdx.x * MULTI_TF;
+  const int g0 = blockIdx.y * MULTI_TG;
+  const int sk = blockIdx.z;
+  const int ns = num_groups * SK;
+  const int chunks_total = (n + MMA_KA - 1) / MMA_KA;
+  const int chunks_per = (chunks_total + SK - 1) / SK;
+  const int a_begin = min(n, sk * chunks_per * MMA_KA);
+  const int a_end = min(n, (sk + 1) * chunks_per * MMA_KA);
+
+  double acc[3][6][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // loader: a stage is 32 rows (frames for A, groups for B) x 48 values (16 atoms x 3), contiguous
+  // in global memory per row; element e of the stage goes to fragment position
+  //   row r = 3 * (e / 48) + comp, tile r / 8, k-step atom / 4:  ((ks * 12 + r / 8) * 32 + (r % 8) * 4 + atom % 4)
+  constexpr int ROW = MMA_KA * 3;
+  constexpr int NQ = MULTI_TF * ROW / MULTI_THREADS;  // 6
+  static_assert(MULTI_TF * ROW % MULTI_THREADS == 0 && MULTI_TF == MULTI_TG, "loader shape");
+  float xr[NQ];
+  double yr[NQ];
+  const float* x_base = pos + (f0 * num_atoms + first_atom) * 3;
+  const double* y_base = ref + (int64_t)g0 * n * 3;
+  uint32_t x_off[NQ], y_off[NQ];
+  int s_dst[NQ], a_rel_x[NQ], a_rel_y[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int e = tid + q * MULTI_THREADS;
+    const int row = e / ROW, rest = e - row * ROW;
+    const int a = rest / 3, c = rest - a * 3;
+    const int r = 3 * row + c;
+    s_dst[q] = (((a >> 2) * (MMA_ROWS / 8) + (r >> 3)) << 5) + ((r & 7) << 2) + (a & 3);
+    a_rel_x[q] = f0 + row < num_frames ? a : (1 << 30);
+    a_rel_y[q] = g0 + row < num_groups ? a : (1 << 30);
+    x_off[q] = (uint32_t)row * (uint32_t)(num_atoms * 3) + (uint32_t)rest;
+    y_off[q] = (uint32_t)row * (uint32_t)(n * 3) + (uint32_t)rest;
+  }
+  auto load_regs = [&](int a0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      xr[q] = a0 + a_rel_x[q] < a_end ? __ldg(x_base + x_off[q] + (int64_t)a0 * 3) : 0.f;
+      yr[q] = a0 + a_rel_y[q] < a_end ? __ldg(y_base + y_off[q] + (int64_t)a0 * 3) : 0.0;
+    }
+  };
+  auto store_regs = [&](int buf) {
+    double* as = &As[buf][0][0][0];
+    double* bs = &Bs[buf][0][0][0];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      as[s_dst[q]] = (double)xr[q];
+      bs[s_dst[q]] = yr[q];
+    }
+  };
+
+  int buf = 0;
+  if (a_begin < a_end) {
+    load_regs(a_begin);
+    store_regs(0);
+  }
+  __syncthreads();
+  for (int a0 = a_begin; a0 < a_end; a0 += MMA_KA) {
+    const bool more = a0 + MMA_KA < a_end;
+    if (more) load_regs(a0 + MMA_KA);
+#pragma unroll
+    for (int ks = 0; ks < MMA_KA / 4; ++ks) {
+      double a[3], b[6];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) a[i] = As[buf][ks][3 * wm + i][lane];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) b[j] = Bs[buf][ks][6 * wn + j][lane];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dmma(acc[i][j], a[i], b[j]);
+    }
+    if (more) store_regs(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // C[row = lane / 4][col = 2 (lane % 4) + h] of tile (3 wm + i, 6 wn + j)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int r = 8 * (3 * wm + i) + (lane >> 2);
+    const int64_t f = f0 + r / 3;
+    const int c = r % 3;
+    if (f >= num_frames) continue;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int q = 8 * (6 * wn + j) + 2 * (lane & 3) + h;
+        const int g = g0 + q / 3, d = q % 3;
+        if (g >= num_groups) continue;
+        partials[((size_t)f * ns + (size_t)g * SK + sk) * 13 + 4 + 3 * c + d] = acc[i][j][h];
+      }
+    }
+  }
+}
+
+// gradient: M = (frame, c) 96 rows, N = 64 atoms, K = (group, d) in stages of 4 groups (12 = 3 k-steps)
+//   g[f][a][c] = F_f (x[f][a][c] - c_f[c]) - sum_(g,d) W[f][g][3c+d] y^[g][a][d]
+// grid = (frame tiles, atom tiles); dynamic shared memory MULTI_GRAD_MMA_SMEM; two CTAs per SM, so
+// that the prologue (x tile, frame constants) and the epilogue (coalesced rows of the gradient) of
+// one CTA run under the tensor-core loop of the other.
+constexpr int MMA_TA = 64;                     // atoms per CTA tile
+constexpr int MMA_KG = 4;                      // groups per stage
+constexpr int MMA_GSTEPS = MMA_KG * 3 / 4;     // k-steps per stage
+constexpr int MMA_A_STAGE = MMA_GSTEPS * (MMA_ROWS / 8) * 32;    // doubles
+constexpr int MMA_B_STAGE = MMA_GSTEPS * (MMA_TA / 8) * 32;
+constexpr int MMA_X_PITCH = MMA_TA * 3 + 4;    // floats per frame row of the x / output tile
+constexpr int MMA_STAGES = 2;                  // double buffer filled through registers
+constexpr size_t MULTI_GRAD_MMA_SMEM = MMA_STAGES * sizeof(double) * (MMA_A_STAGE + MMA_B_STAGE) +
+                                       sizeof(float) * MULTI_TF * MMA_X_PITCH + sizeof(double) * MULTI_TF * 4;
+
+__global__ void __launch_bounds__(MULTI_THREADS, 2)
+    rmsd_multi_gradient_mma_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom,
+                                   int n, const double* __restrict__ ref, int num_groups,
+                                   int64_t num_frames, const double* __restrict__ weights,
+                                   const double* __restrict__ centroid /* [frame][nseg][3], seg 0 */,
+                                   int nseg, float* __restrict__ grad, int accumulate) {
+  extern __shared__ __align__(16) double multi_smem[];
+  double* stage = multi_smem;                                     // [MMA_STAGES][A stage | B stage]
+  float* xs = reinterpret_cast<float*>(stage + MMA_STAGES * (MMA_A_STAGE + MMA_B_STAGE));  // [32][MMA_X_PITCH]
+  double* fc = reinterpret_cast<double*>(xs + MULTI_TF * MMA_X_PITCH);           // [32][4]: c_f, F_f
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;  // row tiles 3 wm .. + 2, atom tiles 4 wn .. 4 wn + 3
+  const int64_t f0 = (int64_t)blockIdx.x * MULTI_TF;
+  const int a0 = blockIdx.y * MMA_TA;
+  const int atoms_here = min(MMA_TA, n - a0);
+
+  // x tile (coalesced rows) and the frame constants; consumed by the epilogue
+  for (int e = tid; e < MULTI_TF * MMA_TA * 3; e += MULTI_THREADS) {
+    const int fl = e / (MMA_TA * 3), rest = e - fl * (MMA_TA * 3);
+    float v = 0.f;
+    if (f0 + fl < num_frames && rest < atoms_here * 3)
+      v = pos[((f0 + fl) * num_atoms + first_atom + a0) * 3 + rest];
+    xs[fl * MMA_X_PITCH + rest] = v;
+  }
+  {
+    // F_f = sum_g factor[f][g]: 8 threads per frame, each a strided eighth of the groups
+    const int fl = tid >> 3, part = tid & 7;
+    const int64_t f = f0 + fl;
+    double sum = 0.0;
+    if (f < num_frames)
+      for (int g = part; g < num_groups; g += 8) sum += __ldg(weights + (f * num_groups + g) * 10 + 9);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    if (part < 4) {
+      double v = sum;
+      if (part < 3) v = f < num_frames ? centroid[(size_t)f * nseg * 3 + part] : 0.0;
+      fc[4 * fl + part] = v;
+    }
+  }
+
+  // loaders (roles fixed per thread).  A stage: 32 frames x 4 groups x 9 values; B stage: 4 groups
+  // x 64 atoms x 3; fragment positions as in the covariance kernel with k = 3 * group + d.
+  constexpr int NA = (MULTI_TF * MMA_KG * 9 + MULTI_THREADS - 1) / MULTI_THREADS;  // 5
+  constexpr int NB = MMA_KG * MMA_TA * 3 / MULTI_THREADS;                          // 3
+  static_assert(MMA_KG * MMA_TA * 3 % MULTI_THREADS == 0, "B loader shape");
+  // (8-byte cp.async copies straight to the fragment positions were tried instead of the register
+  // staging below: 1.24 ms against 1.08 ms per 1024 frames -- one LSU transaction per double)
+  int a_dst[NA], b_dst[NB];
+  int a_src[NA], b_src[NB];  // offsets for group 0 of the stage (32 bits are plenty); < 0: zero
+  int a_gl[NA], b_gl[NB];
+  const double* w_base = weights + f0 * num_groups * 10;
+  const double* y_base = ref + (int64_t)a0 * 3;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) {
+    const int e = tid + q * MULTI_THREADS;
+    const int fl = e / (MMA_KG * 9), rest = e - fl * (MMA_KG * 9);
+    const int gl = rest / 9, v = rest - gl * 9, c = v / 3, d = v - 3 * c;
+    const int r = 3 * fl + c, kk = 3 * gl + d;
+    const bool ok = e < MULTI_TF * MMA_KG * 9 && f0 + fl < num_frames;
+    a_dst[q] = e < MULTI_TF * MMA_KG * 9
+                   ? ((((kk >> 2) * (MMA_ROWS / 8) + (r >> 3)) << 5) + ((r & 7) << 2) + (kk & 3))
+                   : -1;
+    a_src[q] = ok ? (fl * num_groups + gl) * 10 + v : -1;
+    a_gl[q] = gl;
+  }
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int e = tid + q * MULTI_THREADS;
+    const int gl = e / (MMA_TA * 3), rest = e - gl * (MMA_TA * 3);
+    const int al = rest / 3, d = rest - 3 * al, kk = 3 * gl + d;
+    b_dst[q] = (((kk >> 2) * (MMA_TA / 8) + (al >> 3)) << 5) + ((al & 7) << 2) + (kk & 3);
+    b_src[q] = al < atoms_here ? (gl * n + al) * 3 + d : -1;
+    b_gl[q] = gl;
+  }
+  double ar[NA], br[NB];
+  auto load_regs = [&](int g0) {
+#pragma unroll
+    for (int q = 0; q < NA; ++q)
+      ar[q] = a_src[q] >= 0 && g0 + a_gl[q] < num_groups ? __ldg(w_base + a_src[q] + (int64_t)g0 * 10) : 0.0;
+#pragma unroll
+    for (int q = 0; q < NB; ++q)
+      br[q] = b_src[q] >= 0 && g0 + b_gl[q] < num_groups ? __ldg(y_base + b_src[q] + (int64_t)g0 * n * 3) : 0.0;
+  };
+  auto store_regs = [&](int buf) {
+    double* as = stage + (size_t)buf * (MMA_A_STAGE + MMA_B_STAGE);
+    double* bs = as + MMA_A_STAGE;
+#pragma unroll
+    for (int q = 0; q < NA; ++q)
+      if (a_dst[q] >= 0) as[a_dst[q]] = ar[q];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) bs[b_dst[q]] = br[q];
+  };
+
+  double acc[3][4][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  load_regs(0);
+  store_regs(0);
+  __syncthreads();
+  int buf = 0;
+  for (int g0 = 0; g0 < num_groups; g0 += MMA_KG) {
+    const bool more = g0 + MMA_KG < num_groups;
+    if (more) load_regs(g0 + MMA_KG);
+    const double* as = stage + (size_t)buf * (MMA_A_STAGE + MMA_B_STAGE);
+    const double* bs = as + MMA_A_STAGE;
+#pragma unroll
+    for (int ks = 0; ks < MMA_GSTEPS; ++ks) {
+      double a[3], b[4];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) a[i] = as[((ks * (MMA_ROWS / 8) + 3 * wm + i) << 5) + lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = bs[((ks * (MMA_TA / 8) + 4 * wn + j) << 5) + lane];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
+    }
+    if (more) store_regs(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // epilogue: v = F (x - c) - acc in double, written over x in the shared tile, then coalesced rows
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int r = 8 * (3 * wm + i) + (lane >> 2);
+    const int fl = r / 3, c = r - 3 * fl;
+    const double cf = fc[4 * fl + c], big_f = fc[4 * fl + 3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int al = 8 * (4 * wn + j) + 2 * (lane & 3) + h;
+        float* slot = xs + fl * MMA_X_PITCH + al * 3 + c;
+        *slot = (float)(big_f * ((double)*slot - cf) - acc[i][j][h]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < MULTI_TF * MMA_TA * 3; e += MULTI_THREADS) {
+    const int fl = e / (MMA_TA * 3), rest = e - fl * (MMA_TA * 3);
+    if (f0 + fl >= num_frames || rest >= atoms_here * 3) continue;
+    float* out = grad + ((f0 + fl) * num_atoms + first_atom + a0) * 3 + rest;
+    const float v = xs[fl * MMA_X_PITCH + rest];
+    *out = accumulate ? *out + v : v;
+  }
+}
+
 constexpr size_t MULTI_GRAD_SMEM =
     2 * sizeof(double) * (MULTI_KG * MULTI_TF * 10 + MULTI_KG * MULTI_TA * 3);
 

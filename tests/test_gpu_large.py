@@ -307,6 +307,15 @@ def test_path_many_references_one_atom_set(metric, n_group, first, frames, miles
     native.set_option("multi", 1)
     assert torch.allclose(value2._value, value._value, rtol=2e-6, atol=1e-7)
     assert (grad2 - grad).abs().max() <= 2e-6 * grad.abs().max()
+    # the FP64 tensor-core (DMMA) kernels are the default; the register-tiled DFMA kernels they
+    # replace must agree to the rounding of a different summation order
+    assert native.set_option("multi_mma", 0) == 1
+    value3, grad3 = cv.getValueAndGradient(ctx)
+    native.set_option("multi_mma", 1)
+    assert torch.allclose(value3._value, value._value, rtol=1e-6, atol=1e-7)
+    assert (grad3 - grad).abs().max() <= 1e-6 * grad.abs().max()
+    value4, grad4 = cv.getValueAndGradient(ctx)
+    assert torch.equal(value4._value, value._value) and torch.equal(grad4, grad), "not deterministic"
     outside = torch.ones(n, dtype=torch.bool)
     outside[atoms] = False
     assert not grad[:, outside].any()
