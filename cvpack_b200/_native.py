@@ -207,6 +207,14 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     "cvp_peer_wait": (C.c_int, [_vp, _vp]),
     "cvp_peer_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "cvp_peer_buffer_destroy": (C.c_int, [_vp]),
+    "cvp_dcd_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "cvp_dcd_info": (
+        C.c_int,
+        [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int32),
+         C.POINTER(C.c_int32)],
+    ),
+    "cvp_dcd_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int]),
+    "cvp_dcd_close": (C.c_int, [_vp]),
     "cvp_last_error": (C.c_char_p, []),
     "cvp_version": (C.c_int, []),
     "cvp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

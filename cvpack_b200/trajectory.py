@@ -23,8 +23,7 @@ this module is host-side plumbing.
 
 from __future__ import annotations
 
-import concurrent.futures
-import io
+import ctypes as C
 import math
 import os
 import queue
@@ -88,51 +87,36 @@ class DCDFile:
         self.path = os.fspath(path)
         if readThreads is None:
             try:
-                readThreads = min(8, len(os.sched_getaffinity(0)))
+                readThreads = len(os.sched_getaffinity(0))
             except AttributeError:
-                readThreads = min(8, os.cpu_count() or 1)
+                readThreads = os.cpu_count() or 1
         self.readThreads = max(1, int(readThreads))
-        with open(self.path, "rb") as file:
-            head = file.read(92)
-            if len(head) < 92 or struct.unpack("<i", head[:4])[0] != 84 or head[4:8] != b"CORD":
-                raise ValueError(f"{self.path}: not a little-endian CORD DCD file")
-            icntrl = struct.unpack("<20i", head[8:88])
-            if struct.unpack("<i", head[88:92])[0] != 84:
-                raise ValueError(f"{self.path}: corrupt DCD header")
-            self.firstStep, self.interval = icntrl[1], icntrl[2]
-            self.hasBox = icntrl[10] == 1
-            if icntrl[11] == 1:
-                raise ValueError(f"{self.path}: 4-dimensional DCD files are not supported")
-            if icntrl[8] != 0:
-                raise ValueError(f"{self.path}: fixed-atom (X-PLOR) DCD files are not supported")
-            (title_bytes,) = struct.unpack("<i", file.read(4))
-            file.seek(title_bytes, io.SEEK_CUR)
-            if struct.unpack("<i", file.read(4))[0] != title_bytes:
-                raise ValueError(f"{self.path}: corrupt DCD title block")
-            four, num_atoms, four_b = struct.unpack("<3i", file.read(12))
-            if four != 4 or four_b != 4 or num_atoms <= 0:
-                raise ValueError(f"{self.path}: corrupt DCD atom-count block")
-            self.numAtoms = num_atoms
-            self._offset = file.tell()
-            file.seek(0, io.SEEK_END)
-            size = file.tell()
-        fields: t.List[t.Tuple[str, str, t.Tuple[int, ...]]] = []
-        if self.hasBox:
-            fields += [("cell_head", "<i4", ()), ("cell", "<f8", (6,)), ("cell_tail", "<i4", ())]
-        for axis in "xyz":
-            fields += [(axis + "_head", "<i4", ()), (axis, "<f4", (num_atoms,)), (axis + "_tail", "<i4", ())]
-        self._dtype = np.dtype([(n, f, s) if s else (n, f) for n, f, s in fields])
-        frames_by_size = (size - self._offset) // self._dtype.itemsize
-        self.numFrames = int(frames_by_size)
-        self._map = (
-            np.memmap(self.path, dtype=self._dtype, mode="r", offset=self._offset, shape=(self.numFrames,))
-            if self.numFrames > 0
-            else np.zeros(0, dtype=self._dtype)
+        # the file is parsed, mapped and de-interleaved by the native library (csrc/trajio.cu)
+        lib = _native.load()
+        handle = C.c_void_p()
+        _native.check(lib.cvp_dcd_open(self.path.encode(), C.byref(handle)))
+        self._handle: t.Optional[int] = handle.value
+        frames, atoms = C.c_int64(), C.c_int64()
+        has_box, first, interval = C.c_int(), C.c_int32(), C.c_int32()
+        _native.check(
+            lib.cvp_dcd_info(self._handle, C.byref(frames), C.byref(atoms), C.byref(has_box),
+                             C.byref(first), C.byref(interval))
         )
-        if self.numFrames > 0:
-            first = self._map[0]
-            if int(first["x_head"]) != 4 * num_atoms or int(first["z_tail"]) != 4 * num_atoms:
-                raise ValueError(f"{self.path}: unexpected coordinate record size")
+        self.numFrames, self.numAtoms = int(frames.value), int(atoms.value)
+        self.hasBox = bool(has_box.value)
+        self.firstStep, self.interval = int(first.value), int(interval.value)
+
+    def close(self) -> None:
+        """Unmap the file."""
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            _native.load().cvp_dcd_close(handle)
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
 
     def __len__(self) -> int:
         return self.numFrames
@@ -146,8 +130,10 @@ class DCDFile:
     ) -> t.Tuple[np.ndarray, t.Optional[np.ndarray]]:
         """
         Frames ``start .. start+count-1`` as ``[count, N, 3]`` ``float32`` **nm** (into
-        ``positions`` if given: any writable array of that shape, e.g. a view of pinned memory) and
-        their box vectors ``[count, 3, 3]`` ``float64`` nm (``None`` without unit cells).
+        ``positions`` if given: any writable C-contiguous array of that shape, e.g. a view of pinned
+        memory) and their box vectors ``[count, 3, 3]`` ``float64`` nm (``None`` without unit
+        cells).  The X/Y/Z records are de-interleaved by ``cvp_dcd_read`` on ``readThreads`` host
+        threads, straight into the destination.
         """
         if start < 0 or count < 0 or start + count > self.numFrames:
             raise IndexError(f"frames {start}..{start + count - 1} outside 0..{self.numFrames - 1}")
@@ -155,26 +141,18 @@ class DCDFile:
             positions = np.empty((count, self.numAtoms, 3), dtype=np.float32)
         if positions.shape != (count, self.numAtoms, 3) or positions.dtype != np.float32:
             raise ValueError("positions must be a float32 array of shape [count, numAtoms, 3]")
-        block = self._map[start:start + count]
-        scale = np.float32(_ANGSTROM_PER_NM)  # (a correctly rounded quotient, not x * 0.1f)
-
-        def convert(lo: int, hi: int) -> None:
-            for k, axis in enumerate("xyz"):
-                np.divide(block[axis][lo:hi], scale, out=positions[lo:hi, :, k])
-
-        # the strided de-interleave runs at about 1 GB/s per thread; numpy releases the GIL, so large
-        # chunks are split over a few threads (frames are independent)
-        workers = min(self.readThreads, count)
-        if workers > 1 and count * self.numAtoms >= (1 << 20):
-            bounds = np.linspace(0, count, workers + 1).astype(int)
-            with concurrent.futures.ThreadPoolExecutor(workers) as pool:
-                list(pool.map(lambda i: convert(int(bounds[i]), int(bounds[i + 1])), range(workers)))
-        else:
-            convert(0, count)
+        if not positions.flags.c_contiguous or not positions.flags.writeable:
+            raise ValueError("positions must be C-contiguous and writable")
+        cell = np.empty((count, 6), dtype=np.float64) if self.hasBox else None
+        _native.check(
+            _native.load().cvp_dcd_read(
+                self._handle, int(start), int(count), positions.ctypes.data,
+                None if cell is None else cell.ctypes.data, self.readThreads,
+            )
+        )
         boxes = None
-        if self.hasBox:
-            cell = np.asarray(block["cell"], dtype=np.float64)  # A, gamma, B, beta, alpha, C
-            lengths = cell[:, [0, 2, 5]] / _ANGSTROM_PER_NM
+        if cell is not None:
+            lengths = cell[:, [0, 2, 5]] / _ANGSTROM_PER_NM  # A, gamma, B, beta, alpha, C
             raw = cell[:, [4, 3, 1]]  # alpha, beta, gamma
             # CHARMM >= 25 stores cosines, everybody else degrees
             cosines = np.all(np.abs(raw) <= 1.0, axis=1, keepdims=True)
@@ -240,7 +218,22 @@ class NumpyTrajectory:
 
     def __init__(self, positions: t.Any, boxVectors: t.Any = None) -> None:
         if isinstance(positions, (str, os.PathLike)):
-            positions = np.load(os.fspath(positions), mmap_mode="r")
+            path = os.fspath(positions)
+            if path.lower().endswith(".npz"):
+                # an archive of arrays: coordinates under "positions" / "xyz" / "coordinates" (nm),
+                # optional box under "box" / "boxVectors" / "unitcell_vectors"
+                archive = np.load(path)
+                key = next((k for k in ("positions", "xyz", "coordinates") if k in archive.files), None)
+                if key is None:
+                    raise ValueError(f"{path}: no 'positions', 'xyz' or 'coordinates' array in the archive")
+                positions = archive[key]
+                if boxVectors is None:
+                    box_key = next(
+                        (k for k in ("box", "boxVectors", "unitcell_vectors") if k in archive.files), None
+                    )
+                    boxVectors = None if box_key is None else archive[box_key]
+            else:
+                positions = np.load(path, mmap_mode="r")
         if isinstance(positions, torch.Tensor):
             positions = positions.detach().cpu().numpy()
         if positions.ndim != 3 or positions.shape[2] != 3:
@@ -285,7 +278,7 @@ class NumpyTrajectory:
 
 
 def open_trajectory(source: t.Any, boxVectors: t.Any = None) -> t.Any:
-    """A :class:`DCDFile` for ``*.dcd`` paths, else a :class:`NumpyTrajectory`."""
+    """A :class:`DCDFile` for ``*.dcd`` paths, else a :class:`NumpyTrajectory` (arrays, ``.npy``, ``.npz``)."""
     if hasattr(source, "read") and hasattr(source, "numFrames"):
         return source
     if isinstance(source, (str, os.PathLike)) and os.fspath(source).lower().endswith(".dcd"):

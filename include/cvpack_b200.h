@@ -332,6 +332,21 @@ int cvp_peer_wait(cvp_peer_buffer* buffer, void* stream);
 int cvp_peer_status(cvp_peer_buffer* buffer, int* timed_out);
 int cvp_peer_buffer_destroy(cvp_peer_buffer* buffer);
 
+/* ---- trajectory ingestion (host side) --------------------------------- */
+/* The callers of the reference evaluate one frame per reported step (reporting/cv_writer.py:102-109);
+ * the batched analogue reads stored frames.  A DCD frame holds X, Y, Z as separate float32 records
+ * in Angstrom: cvp_dcd_read maps the file and converts frames first .. first+count-1 to interleaved
+ * [count][N][3] float nm (x / 10.0f) in a caller-owned host buffer (pinned memory for the
+ * pipeline), split over `threads` host threads (<= 0: one per core); `cell` (may be NULL) receives
+ * the raw unit-cell records [count][6] (A, gamma, B, beta, alpha, C).  No GPU involved.            */
+typedef struct cvp_dcd cvp_dcd;
+int cvp_dcd_open(const char* path, cvp_dcd** out);
+int cvp_dcd_info(const cvp_dcd* file, int64_t* num_frames, int64_t* num_atoms, int* has_box,
+                 int32_t* first_step, int32_t* interval);
+int cvp_dcd_read(const cvp_dcd* file, int64_t first, int64_t count, float* positions, double* cell,
+                 int threads);
+int cvp_dcd_close(cvp_dcd* file);
+
 /* ---- diagnostics ------------------------------------------------------------------------------- */
 const char* cvp_last_error(void);
 int cvp_version(void);

@@ -86,9 +86,11 @@ def test_dcd_triclinic_box_round_trip(tmp_path, cosines):
     if cosines:  # CHARMM >= 25 stores the cosines of the angles instead of degrees
         dcd = DCDFile(path)
         raw = bytearray(path.read_bytes())
-        frame = dcd._dtype.itemsize  # pylint: disable=protected-access
+        frame = 56 + 3 * (8 + 4 * dcd.numAtoms)
+        data_offset = len(raw) - 3 * frame
+        dcd.close()
         for b in range(3):
-            at = dcd._offset + b * frame + 4  # pylint: disable=protected-access
+            at = data_offset + b * frame + 4
             cell = list(struct.unpack("<6d", raw[at:at + 48]))
             for k in (1, 3, 4):
                 cell[k] = np.cos(np.deg2rad(cell[k]))
@@ -273,3 +275,52 @@ def test_bias_forces_in_place(precision):
         cvbias.accumulateBiasForces(forces, forces[:, :10].contiguous(), torch.zeros(walkers))
     with pytest.raises(ValueError):
         cvbias.accumulateBiasForces(forces.cpu(), forces.cpu(), torch.zeros(walkers))
+
+
+def test_native_dcd_reader_matches_a_python_reading_of_the_file(tmp_path):
+    """cvp_dcd_read (csrc/trajio.cu: mmap + host threads) against numpy on the raw bytes: every
+    coordinate is the correctly rounded quotient x / 10, whatever the thread count and the window."""
+    rng = np.random.default_rng(9)
+    frames, atoms = 37, 1013
+    x = rng.normal(size=(frames, atoms, 3)) * 3.0
+    path = tmp_path / "big.dcd"
+    DCDFile.write(path, x, boxVectors=np.diag([7.0, 8.0, 9.0]), firstStep=100, interval=10)
+    raw = path.read_bytes()
+    frame_bytes = 56 + 3 * (8 + 4 * atoms)
+    offset = len(raw) - frames * frame_bytes
+    expected = np.empty((frames, atoms, 3), dtype=np.float32)
+    for b in range(frames):
+        base = offset + b * frame_bytes + 56
+        for k in range(3):
+            record = np.frombuffer(raw, dtype="<f4", count=atoms, offset=base + k * (8 + 4 * atoms) + 4)
+            expected[b, :, k] = record / np.float32(10.0)
+    for threads in (1, 3, 64):
+        dcd = DCDFile(path, readThreads=threads)
+        assert (dcd.numFrames, dcd.numAtoms, dcd.hasBox, dcd.firstStep, dcd.interval) == (frames, atoms, True, 100, 10)
+        got, boxes = dcd.read(0, frames)
+        assert np.array_equal(got, expected)
+        assert np.array_equal(boxes[5], np.diag([7.0, 8.0, 9.0]))
+        window = np.zeros((11, atoms, 3), dtype=np.float32)
+        dcd.read(20, 11, positions=window)
+        assert np.array_equal(window, expected[20:31])
+        with pytest.raises(IndexError):
+            dcd.read(30, 8)
+        with pytest.raises(ValueError):
+            dcd.read(0, 2, positions=np.zeros((2, atoms, 3), dtype=np.float64))
+        dcd.close()
+
+
+def test_npz_archives(tmp_path):
+    rng = np.random.default_rng(10)
+    x = rng.normal(size=(5, 7, 3)).astype(np.float32)
+    box = np.diag([2.0, 2.5, 3.0])
+    np.savez(tmp_path / "a.npz", xyz=x, unitcell_vectors=np.broadcast_to(box, (5, 3, 3)))
+    np.savez(tmp_path / "b.npz", positions=x)
+    np.savez(tmp_path / "c.npz", other=x)
+    traj = open_trajectory(tmp_path / "a.npz")
+    got, boxes = traj.read(1, 3)
+    assert np.array_equal(got, x[1:4]) and np.array_equal(boxes[0], box) and traj.hasBox
+    traj = open_trajectory(tmp_path / "b.npz")
+    assert traj.numFrames == 5 and not traj.hasBox
+    with pytest.raises(ValueError, match="no 'positions'"):
+        open_trajectory(tmp_path / "c.npz")
