@@ -122,6 +122,41 @@ class ClockSampler:
                 self.proc.kill()
 
 
+def pin_to_gpu_numa_node(device_index: int):
+    """Restrict this process to the host cores nvidia-smi lists as local to the GPU (`nvidia-smi topo
+    -m`, column "CPU Affinity") before any pinned memory is allocated: with one rank per GPU, first
+    touch then places the staging buffers of the host path on the GPU's own NUMA node instead of
+    wherever torchrun started the rank.  Returns the core list as a string, or None."""
+    try:
+        text = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    header = next((line for line in text.splitlines() if "CPU Affinity" in line), None)
+    row = next((line for line in text.splitlines() if line.split("\t")[0].strip() == f"GPU{device_index}"), None)
+    if header is None or row is None:
+        return None
+    names = [c.strip() for c in header.split("\t")]
+    cells = [c.strip() for c in row.split("\t")]
+    # the header row has an empty first cell: align from the right-hand columns by name
+    try:
+        column = names.index("CPU Affinity")
+        spec = cells[column] if len(cells) == len(names) else cells[column - (len(names) - len(cells))]
+    except (ValueError, IndexError):
+        return None
+    cores = set()
+    try:
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cores.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cores & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+    except (ValueError, OSError, AttributeError):
+        return None
+    return spec
+
+
 def measured_peaks() -> dict:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -735,6 +770,7 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")
+    affinity = pin_to_gpu_numa_node(local_rank) if distributed and not args.no_affinity else None
 
     frames = args.frames or spec["frames"]
     n = spec["atoms"]
@@ -905,7 +941,9 @@ def run_ours(args) -> None:
             "parallelism": f"frames sharded over {world} GPU(s), values all-gathered",
         },
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "host_gb_per_s_per_rank_each_way": h2d * e2e_steps / e2e_s / 1e9,
+                "cpu_affinity_rank0": affinity},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
@@ -936,6 +974,8 @@ def main() -> None:
     parser.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the config's)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-extras", action="store_true", help="headline only")
+    parser.add_argument("--no-affinity", action="store_true",
+                        help="N > 1: do not pin the ranks to the host cores local to their GPU")
     parser.add_argument("--extras", default="all", help="comma-separated subset of the extra records "
                         "(rmsd,rg,path,helix_rmsd,helix_torsion,walkers_contacts,walkers_composite_rmsd,contacts_fp64)")
     args = parser.parse_args()

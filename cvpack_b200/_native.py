@@ -203,6 +203,9 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     "cvp_peer_buffer_open": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cvp_peer_buffer_local": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "cvp_peer_push": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int32, _vp]),
+    "cvp_peer_push_rows": (
+        C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp]
+    ),
     "cvp_peer_signal": (C.c_int, [_vp, _vp]),
     "cvp_peer_wait": (C.c_int, [_vp, _vp]),
     "cvp_peer_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),

@@ -83,6 +83,22 @@ __global__ void peer_push_active_kernel(const T* __restrict__ src, PeerPointers 
   }
 }
 
+// rows: bytes [row_offset, row_offset + row_bytes) of every frame (a contiguous run of atoms), as
+// vectors of sizeof(V) bytes; frame b of the source lands in frame first_frame + b of every rank
+template <typename V>
+__global__ void peer_push_rows_kernel(const char* __restrict__ src, PeerPointers peers, int world,
+                                      int64_t first_frame, size_t frame_bytes, size_t row_offset,
+                                      int row_vectors, int64_t total) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t frame = t / row_vectors;
+    const size_t within = row_offset + (size_t)(t - frame * row_vectors) * sizeof(V);
+    const V v = *reinterpret_cast<const V*>(src + (size_t)frame * frame_bytes + within);
+    const size_t at = (size_t)(first_frame + frame) * frame_bytes + within;
+    for (int p = 0; p < world; ++p) *reinterpret_cast<V*>(peers.base[p] + at) = v;
+  }
+}
+
 __global__ void peer_signal_kernel(PeerPointers peers, int world, int rank, size_t payload,
                                    uint32_t epoch) {
   // everything this stream wrote before is ordered before the flags, for observers on any GPU
@@ -228,6 +244,40 @@ int cvp_peer_push(cvp_peer_buffer* buf, int dtype, const void* src, int64_t firs
                                                              buf->world, offset, total);
     }
   }
+  CVP_LAUNCH_CHECK();
+  return CVP_OK;
+}
+
+int cvp_peer_push_rows(cvp_peer_buffer* buf, int dtype, const void* src, int64_t first_frame,
+                       int64_t num_frames, int64_t num_atoms, int64_t first_atom, int64_t atom_count,
+                       void* stream) {
+  CVP_REQUIRE(buf != nullptr && src != nullptr, "null argument");
+  CVP_REQUIRE(dtype == CVP_F32 || dtype == CVP_F64, "dtype must be CVP_F32 or CVP_F64");
+  CVP_REQUIRE(first_frame >= 0 && num_frames >= 0 && num_atoms > 0 && first_atom >= 0 && atom_count >= 0 &&
+                  first_atom + atom_count <= num_atoms,
+              "bad frame or atom range");
+  const size_t es = dtype == CVP_F32 ? 4 : 8;
+  const size_t frame_bytes = (size_t)num_atoms * 3 * es;
+  CVP_REQUIRE((size_t)(first_frame + num_frames) * frame_bytes <= buf->bytes,
+              "frames do not fit the gather buffer");
+  if (num_frames == 0 || atom_count == 0) return CVP_OK;
+  PeerPointers peers;
+  int status = fill_pointers(buf, &peers);
+  if (status != CVP_OK) return status;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t row_offset = (size_t)first_atom * 3 * es, row_bytes = (size_t)atom_count * 3 * es;
+  const bool wide = aligned16(src) && frame_bytes % 16 == 0 && row_offset % 16 == 0 && row_bytes % 16 == 0;
+  const size_t vec = wide ? 16 : 4;
+  const int64_t total = num_frames * (int64_t)(row_bytes / vec);
+  const unsigned blocks = (unsigned)std::min<int64_t>(div_up(total, 256), 148 * 8);
+  if (wide)
+    peer_push_rows_kernel<uint4><<<blocks, 256, 0, st>>>(static_cast<const char*>(src), peers, buf->world,
+                                                        first_frame, frame_bytes, row_offset,
+                                                        (int)(row_bytes / 16), total);
+  else
+    peer_push_rows_kernel<uint32_t><<<blocks, 256, 0, st>>>(static_cast<const char*>(src), peers,
+                                                           buf->world, first_frame, frame_bytes,
+                                                           row_offset, (int)(row_bytes / 4), total);
   CVP_LAUNCH_CHECK();
   return CVP_OK;
 }

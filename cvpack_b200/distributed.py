@@ -126,6 +126,7 @@ class PeerGather:
         self._buffers: t.List[int] = []
         self._tensors: t.List[torch.Tensor] = []
         self._turn = 0
+        self._run_cache: t.Dict[t.Tuple[int, int], t.Optional[t.List[t.Tuple[int, int]]]] = {}
         lib = _native.load()
         element = 4 if dtype == torch.float32 else 8
         nbytes = self._shape[0] * self._shape[1] * 3 * element
@@ -169,6 +170,18 @@ class PeerGather:
         if active_atoms is not None:
             if active_atoms.dtype != torch.int32 or not active_atoms.is_cuda:
                 raise ValueError("active_atoms must be an int32 CUDA tensor")
+            runs = self._runs(active_atoms)
+            if runs is not None:
+                # the active atoms are a few contiguous runs: wide row copies instead of a scatter
+                for first_atom, atom_count in runs:
+                    _native.check(
+                        _native.load().cvp_peer_push_rows(
+                            self._buffers[self._turn], self._cvp_dtype, gradient.data_ptr(),
+                            int(first_frame), int(gradient.shape[0]), self._shape[1], first_atom,
+                            atom_count, stream,
+                        )
+                    )
+                return
             active_ptr, count = active_atoms.data_ptr(), int(active_atoms.numel())
         _native.check(
             _native.load().cvp_peer_push(
@@ -176,6 +189,17 @@ class PeerGather:
                 int(gradient.shape[0]), self._shape[1], active_ptr, count, stream,
             )
         )
+
+    def _runs(self, active_atoms: torch.Tensor) -> t.Optional[t.List[t.Tuple[int, int]]]:
+        """Contiguous runs (first atom, count) of a sorted atom list, or None if there are many."""
+        key = (active_atoms.data_ptr(), int(active_atoms.numel()))
+        if key not in self._run_cache:
+            atoms = active_atoms.cpu().numpy()
+            breaks = [0] + [int(k) for k in (atoms[1:] != atoms[:-1] + 1).nonzero()[0] + 1] + [len(atoms)]
+            runs = [(int(atoms[a]), b - a) for a, b in zip(breaks[:-1], breaks[1:]) if b > a]
+            sorted_unique = bool((atoms[1:] > atoms[:-1]).all()) if len(atoms) > 1 else True
+            self._run_cache[key] = runs if sorted_unique and len(runs) <= 8 else None
+        return self._run_cache[key]
 
     def finish(self, stream: t.Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """Stream-ordered barrier: after it (on that stream) the buffer holds every rank's frames.

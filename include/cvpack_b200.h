@@ -327,6 +327,12 @@ int cvp_peer_buffer_local(cvp_peer_buffer* buffer, void** ptr, int64_t* bytes);
 int cvp_peer_push(cvp_peer_buffer* buffer, int dtype, const void* src /* [count][N][3] device */,
                   int64_t first_frame, int64_t num_frames, int64_t num_atoms,
                   const int32_t* active /* device, or NULL = dense */, int32_t num_active, void* stream);
+/* The same for one contiguous run of atoms [first_atom, first_atom + atom_count) of every frame:
+ * 16-byte vectors when the run is aligned -- the fast form of the compact push when the active
+ * atoms form a few runs (the binding splits the list).                                              */
+int cvp_peer_push_rows(cvp_peer_buffer* buffer, int dtype, const void* src, int64_t first_frame,
+                       int64_t num_frames, int64_t num_atoms, int64_t first_atom, int64_t atom_count,
+                       void* stream);
 int cvp_peer_signal(cvp_peer_buffer* buffer, void* stream);
 int cvp_peer_wait(cvp_peer_buffer* buffer, void* stream);
 int cvp_peer_status(cvp_peer_buffer* buffer, int* timed_out);

@@ -69,6 +69,18 @@ def _worker(rank: int, world: int, port: int, num_frames: int) -> None:
                 gathered = peer.finish()
             torch.cuda.current_stream(device).wait_stream(side)
             assert torch.equal(gathered, ref_grad), f"rank {rank}: peer gather differs (active={use_active})"
+        # an atom list with many short runs takes the scatter kernel instead of the row copies
+        scattered = torch.arange(1, n, 3, device=device, dtype=torch.int32)
+        sparse = torch.zeros_like(grad)
+        sparse[:, scattered.long()] = grad[:, : scattered.numel()]
+        expected = distributed.all_gather_gradients(sparse, num_frames)
+        peer.tensor().zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        peer.push(sparse, begin, scattered)
+        gathered = peer.finish()
+        torch.cuda.synchronize()
+        assert torch.equal(gathered, expected), f"rank {rank}: scattered peer gather differs"
         assert not peer.timed_out()
         dist.barrier()
         peer.close()
