@@ -391,3 +391,42 @@ def test_symmetric_sweep_dilute_frames():
         assert np.array_equal(g[b] != 0, ref_grad[b] != 0)
     # Newton's third law holds to the quantum of the accumulators, frame by frame
     assert np.abs(g[dilute].sum(axis=1)).max() <= 1e-5 * largest[dilute].max() * np.sqrt(n)
+
+
+def test_path_in_rmsd_space_at_config_size():
+    """BASELINE configs[3] at full size -- 64 milestones x 20 000 atoms -- on a few frames against the
+    NumPy oracle (progress and deviation; the FP64 tensor-core contractions of rmsd_multi.cuh)."""
+    from scripts import workloads
+
+    device = torch.device("cuda:0")
+    cv, system, x, _, info = workloads.path_rmsd(3, 4, device)
+    deviation = cvpack.PathInRMSDSpace(cvpack.path.deviation, cv._args["milestones"], 20000, info["sigma"])  # pylint: disable=protected-access
+    deviation.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x)
+    for variable in (cv, deviation):
+        native = ctx._native_cv(variable)  # pylint: disable=protected-access
+        native.set_option("time_kernels", 1)
+        helpers.check_against_oracle(variable, system, x.double().cpu().numpy(), None, "single", 1e-5, 1e-5, context=ctx)
+        assert native.kernel_time("rmsd_multi_cov")[1] >= 1
+    # the progress variable recovers where along the path the frames were generated
+    s = cv.getValue(ctx)._value.double().cpu().numpy() * 63
+    assert np.abs(s - info["generated_position"].double().cpu().numpy()).max() < 0.6
+
+
+def test_walker_batch_at_config_shape():
+    """BASELINE configs[4] shape: 23 000-atom walkers, NumberOfContacts 2 500 x 2 500 (periodic) and a
+    two-body CompositeRMSD (1 500 + 1 000 atoms), against the oracles."""
+    from scripts import workloads
+
+    device = torch.device("cuda:0")
+    cvs, system, x, box, _ = workloads.walkers(6, 8, device)
+    ctx = cvpack.BatchContext(system, x, box)
+    stored = ctx.getPositions().double().cpu().numpy()
+    value, grad = cvs["contacts"].getValueAndGradient(ctx)
+    ref_value, ref_grad = c_oracle.contacts_batch(stored, range(0, 2500), range(2500, 5000), (), np.diag(box),
+                                                  r0=0.6, rc=1.2, rs=0.9, cells=True)
+    v, g = value._value.double().cpu().numpy(), grad.double().cpu().numpy()
+    assert np.abs(v - ref_value).max() <= 1e-5 * np.abs(ref_value).max()
+    assert np.abs(g - ref_grad).max() <= 1e-5 * np.abs(ref_grad).max()
+    assert not g[:, 5000:].any()
+    helpers.check_against_oracle(cvs["composite"], system, stored, np.diag(box), "single", 1e-5, 1e-5, context=ctx)
