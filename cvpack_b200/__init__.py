@@ -32,7 +32,7 @@ from .sheet_rmsd_content import SheetRMSDContent  # noqa: F401
 from .shortest_distance import ShortestDistance  # noqa: F401
 from .torsion import Torsion  # noqa: F401
 from .torsion_similarity import TorsionSimilarity  # noqa: F401
-from .trajectory import DCDFile, NumpyTrajectory, TrajectoryEvaluator  # noqa: F401
+from .trajectory import DCDFile, NumpyTrajectory, TrajectoryEvaluator, XTCFile  # noqa: F401
 
 __all__ = [
     "Angle",

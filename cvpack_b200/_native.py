@@ -218,6 +218,13 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     ),
     "cvp_dcd_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int]),
     "cvp_dcd_close": (C.c_int, [_vp]),
+    "cvp_xtc_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "cvp_xtc_info": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    "cvp_xtc_read": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int]),
+    "cvp_xtc_close": (C.c_int, [_vp]),
+    "cvp_xtc_write": (
+        C.c_int, [C.c_char_p, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_float]
+    ),
     "cvp_last_error": (C.c_char_p, []),
     "cvp_version": (C.c_int, []),
     "cvp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

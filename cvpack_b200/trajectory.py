@@ -10,6 +10,8 @@ to the GPU in chunks and writes the same table, one row per frame:
 * :class:`DCDFile` reads and writes CHARMM/NAMD DCD files (the format OpenMM's ``DCDReporter``
   produces: ``CORD`` header, optional 48-byte unit-cell record, X/Y/Z ``float32`` records in
   Angstrom per frame).  Frames have a fixed size, so chunks are random-access views of a memory map.
+* :class:`XTCFile` reads and writes GROMACS XTC files (compressed integer coordinates in nm;
+  variable-size frames, indexed once on opening and decoded by host threads).
 * :class:`NumpyTrajectory` wraps an ``[B, N, 3]`` array (nm) in memory or memory-mapped from ``.npy``.
 * :class:`TrajectoryEvaluator` runs the chunks through a two-deep pipeline: a reader thread fills
   pinned buffer ``k+1`` (de-interleaving X/Y/Z, Angstrom -> nm) while the copy stream uploads
@@ -213,6 +215,143 @@ class DCDFile:
                     file.write(marker + np.ascontiguousarray(frame[:, k]).tobytes() + marker)
 
 
+class XTCFile:
+    """
+    Random-access reader (and writer) of a GROMACS XTC trajectory: compressed coordinates in nm,
+    a 3x3 box, step and time per frame.  Frames have variable size, so opening the file walks the
+    frame headers once (``cvp_xtc_open`` keeps the offset index); chunks are then decoded by
+    ``readThreads`` host threads straight into the destination (``csrc/xtc.cu``).
+
+    Attributes
+    ----------
+    numFrames, numAtoms
+        Sizes found in the file (a truncated last frame is ignored).
+    precision
+        The writer's rounding (integers per nm, usually 1000); 0 for files of at most 9 atoms,
+        which are stored uncompressed.
+    hasBox
+        Always true: every XTC frame carries box vectors (all zeros when the writer had none).
+    """
+
+    hasBox = True
+
+    def __init__(self, path: t.Union[str, os.PathLike], readThreads: t.Optional[int] = None) -> None:
+        self.path = os.fspath(path)
+        if readThreads is None:
+            try:
+                readThreads = len(os.sched_getaffinity(0))
+            except AttributeError:
+                readThreads = os.cpu_count() or 1
+        self.readThreads = max(1, int(readThreads))
+        lib = _native.load()
+        handle = C.c_void_p()
+        _native.check(lib.cvp_xtc_open(self.path.encode(), C.byref(handle)))
+        self._handle: t.Optional[int] = handle.value
+        frames, atoms, precision = C.c_int64(), C.c_int64(), C.c_float()
+        _native.check(lib.cvp_xtc_info(self._handle, C.byref(frames), C.byref(atoms), C.byref(precision)))
+        self.numFrames, self.numAtoms = int(frames.value), int(atoms.value)
+        self.precision = float(precision.value)
+
+    def close(self) -> None:
+        """Unmap the file."""
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            _native.load().cvp_xtc_close(handle)
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    def __len__(self) -> int:
+        return self.numFrames
+
+    def read(
+        self,
+        start: int,
+        count: int,
+        positions: t.Optional[np.ndarray] = None,
+        boxVectors: t.Optional[np.ndarray] = None,
+    ) -> t.Tuple[np.ndarray, t.Optional[np.ndarray]]:
+        """Same contract as :meth:`DCDFile.read`; a file whose boxes are all zero returns ``None``."""
+        positions, boxes, _, _ = self.readFrames(start, count, positions)
+        if not boxes.any():
+            return positions, None
+        if boxVectors is not None:
+            boxVectors[...] = boxes
+            boxes = boxVectors
+        return positions, boxes
+
+    def readFrames(
+        self, start: int, count: int, positions: t.Optional[np.ndarray] = None
+    ) -> t.Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """Positions ``[count, N, 3]`` nm, boxes ``[count, 3, 3]`` nm, steps ``[count]``, times ``[count]`` (ps)."""
+        if start < 0 or count < 0 or start + count > self.numFrames:
+            raise IndexError(f"frames {start}..{start + count - 1} outside 0..{self.numFrames - 1}")
+        if positions is None:
+            positions = np.empty((count, self.numAtoms, 3), dtype=np.float32)
+        if positions.shape != (count, self.numAtoms, 3) or positions.dtype != np.float32:
+            raise ValueError("positions must be a float32 array of shape [count, numAtoms, 3]")
+        if not positions.flags.c_contiguous or not positions.flags.writeable:
+            raise ValueError("positions must be C-contiguous and writable")
+        boxes = np.zeros((count, 3, 3), dtype=np.float64)
+        steps = np.zeros(count, dtype=np.int32)
+        times = np.zeros(count, dtype=np.float32)
+        _native.check(
+            _native.load().cvp_xtc_read(
+                self._handle, int(start), int(count), positions.ctypes.data, boxes.ctypes.data,
+                steps.ctypes.data, times.ctypes.data, self.readThreads,
+            )
+        )
+        return positions, boxes, steps, times
+
+    @staticmethod
+    def write(  # pylint: disable=too-many-arguments
+        path: t.Union[str, os.PathLike],
+        positions: t.Any,
+        boxVectors: t.Any = None,
+        steps: t.Any = None,
+        times: t.Any = None,
+        precision: float = 1000.0,
+        append: bool = False,
+    ) -> None:
+        """
+        Write ``positions`` (``[B, N, 3]`` nm) with optional box vectors (``[3]``, ``[3, 3]`` or
+        ``[B, 3, 3]`` nm), steps and times (ps) as XTC frames rounded to ``1/precision`` nm.
+        """
+        pos = np.ascontiguousarray(positions, dtype=np.float32)
+        if pos.ndim == 2:
+            pos = pos[None]
+        if pos.ndim != 3 or pos.shape[2] != 3:
+            raise ValueError("positions must have shape [B, N, 3]")
+        frames, atoms = pos.shape[0], pos.shape[1]
+        box = None
+        if boxVectors is not None:
+            box = np.asarray(boxVectors, dtype=np.float64)
+            if box.shape == (3,):
+                box = np.diag(box)
+            if box.ndim == 2:
+                box = np.broadcast_to(box, (frames, 3, 3))
+            if box.shape != (frames, 3, 3):
+                raise ValueError("boxVectors must have shape [3], [3, 3] or [B, 3, 3]")
+            box = np.ascontiguousarray(box)
+        step_array = None if steps is None else np.ascontiguousarray(steps, dtype=np.int32)
+        time_array = None if times is None else np.ascontiguousarray(times, dtype=np.float32)
+        for name, array in (("steps", step_array), ("times", time_array)):
+            if array is not None and array.shape != (frames,):
+                raise ValueError(f"{name} must have shape [B]")
+        _native.check(
+            _native.load().cvp_xtc_write(
+                os.fspath(path).encode(), int(bool(append)), frames, atoms, pos.ctypes.data,
+                None if box is None else box.ctypes.data,
+                None if step_array is None else step_array.ctypes.data,
+                None if time_array is None else time_array.ctypes.data,
+                float(precision),
+            )
+        )
+
+
 class NumpyTrajectory:
     """Frames held in (or memory-mapped from) an ``[B, N, 3]`` array in nm, optional boxes."""
 
@@ -278,11 +417,13 @@ class NumpyTrajectory:
 
 
 def open_trajectory(source: t.Any, boxVectors: t.Any = None) -> t.Any:
-    """A :class:`DCDFile` for ``*.dcd`` paths, else a :class:`NumpyTrajectory` (arrays, ``.npy``, ``.npz``)."""
+    """A :class:`DCDFile` / :class:`XTCFile` for ``*.dcd`` / ``*.xtc`` paths, else a :class:`NumpyTrajectory` (arrays, ``.npy``, ``.npz``)."""
     if hasattr(source, "read") and hasattr(source, "numFrames"):
         return source
     if isinstance(source, (str, os.PathLike)) and os.fspath(source).lower().endswith(".dcd"):
         return DCDFile(source)
+    if isinstance(source, (str, os.PathLike)) and os.fspath(source).lower().endswith(".xtc"):
+        return XTCFile(source)
     return NumpyTrajectory(source, boxVectors)
 
 

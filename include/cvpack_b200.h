@@ -353,6 +353,20 @@ int cvp_dcd_read(const cvp_dcd* file, int64_t first, int64_t count, float* posit
                  int threads);
 int cvp_dcd_close(cvp_dcd* file);
 
+/* GROMACS XTC (libxdrf / xdrfile compressed coordinates, big-endian XDR; nm): frames have variable
+ * size, cvp_xtc_open walks the headers once and keeps an offset index; cvp_xtc_read decodes frames
+ * first .. first+count-1 on `threads` host threads straight into positions [count][N][3] float nm
+ * and fills box [count][9] (rows a, b, c; nm), steps [count], times [count] (ps) when not NULL.
+ * cvp_xtc_write is the matching encoder (precision <= 0: 1000 per nm; box/steps/times may be NULL). */
+typedef struct cvp_xtc cvp_xtc;
+int cvp_xtc_open(const char* path, cvp_xtc** out);
+int cvp_xtc_info(const cvp_xtc* file, int64_t* num_frames, int64_t* num_atoms, float* precision);
+int cvp_xtc_read(const cvp_xtc* file, int64_t first, int64_t count, float* positions, double* box,
+                 int32_t* steps, float* times, int threads);
+int cvp_xtc_close(cvp_xtc* file);
+int cvp_xtc_write(const char* path, int append, int64_t count, int64_t num_atoms, const float* positions,
+                  const double* box, const int32_t* steps, const float* times, float precision);
+
 /* ---- diagnostics ------------------------------------------------------------------------------- */
 const char* cvp_last_error(void);
 int cvp_version(void);

@@ -10,8 +10,8 @@ import torch
 
 import cvpack_b200 as cvpack
 from cvpack_b200 import bias as cvbias
-from cvpack_b200.trajectory import DCDFile, NumpyTrajectory, TrajectoryEvaluator, open_trajectory
-from tests import helpers
+from cvpack_b200.trajectory import DCDFile, NumpyTrajectory, TrajectoryEvaluator, XTCFile, open_trajectory
+from tests import helpers, xtc_python
 
 
 def _frames(rng, frames, atoms, scale=2.0):
@@ -178,7 +178,8 @@ def test_bias_functions_against_finite_differences():
 # ---- GPU -------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("with_box", [False, True])
-def test_streamed_dcd_matches_whole_batch_and_oracle(tmp_path, with_box):
+@pytest.mark.parametrize("fmt", ["dcd", "xtc"])
+def test_streamed_file_matches_whole_batch_and_oracle(tmp_path, with_box, fmt):
     rng = np.random.default_rng(11)
     frames, n = 37, 60  # ragged last chunk: 37 = 3 * 10 + 7
     box = np.array([3.0, 3.2, 3.4])
@@ -190,12 +191,13 @@ def test_streamed_dcd_matches_whole_batch_and_oracle(tmp_path, with_box):
     torsion = cvpack.Torsion(1, 5, 9, 13, pbc=with_box, name="phi")
     for cv in (rg, contacts, torsion):
         cv.addToSystem(system)
-    path = tmp_path / "traj.dcd"
+    path = tmp_path / f"traj.{fmt}"
     boxes = None
     if with_box:  # a different (rectangular) box per frame
         boxes = np.stack([np.diag(box * (1.0 + 0.01 * b)) for b in range(frames)])
-    DCDFile.write(path, x, boxVectors=boxes)
-    stored, stored_box = DCDFile(path).read(0, frames)
+    file_class = DCDFile if fmt == "dcd" else XTCFile
+    file_class.write(path, x, boxVectors=boxes)
+    stored, stored_box = file_class(path).read(0, frames)
 
     evaluator = TrajectoryEvaluator(system, [rg, contacts, torsion], value=True, emass=True, chunkFrames=10)
     table = evaluator.evaluate(str(path))
@@ -324,3 +326,119 @@ def test_npz_archives(tmp_path):
     assert traj.numFrames == 5 and not traj.hasBox
     with pytest.raises(ValueError, match="no 'positions'"):
         open_trajectory(tmp_path / "c.npz")
+
+
+# ---- XTC (GROMACS compressed coordinates) -----------------------------------------------------------
+def _water_box(rng, molecules, edge):
+    """Three-site molecules (sites within 0.1 nm of the first) scattered in a box: the case the
+    format's run coding is made for."""
+    centres = rng.uniform(0.0, edge, size=(molecules, 1, 3))
+    sites = centres + np.concatenate([np.zeros((molecules, 1, 3)), rng.normal(0, 0.05, (molecules, 2, 3))], axis=1)
+    return sites.reshape(-1, 3)
+
+
+def test_xtc_uncompressed_frame_is_the_documented_byte_layout(tmp_path):
+    # <= 9 atoms: magic 1995, natoms, step, time, 9 box floats, natoms again, raw floats; big-endian
+    x = np.arange(15, dtype=np.float32).reshape(1, 5, 3) * np.float32(0.125) - np.float32(0.5)
+    box = np.array([[3.0, 0, 0], [0.5, 4.0, 0], [0.25, 0.75, 5.0]])
+    path = tmp_path / "small.xtc"
+    XTCFile.write(path, x, box, steps=[42], times=[8.5])
+    expected = struct.pack(">iiif", 1995, 5, 42, 8.5) + struct.pack(">9f", *box.ravel())
+    expected += struct.pack(">i", 5) + struct.pack(">15f", *x.ravel())
+    assert path.read_bytes() == expected
+    xtc = XTCFile(path)
+    assert (len(xtc), xtc.numAtoms, xtc.precision) == (1, 5, 0.0)
+    pos, boxes, steps, times = xtc.readFrames(0, 1)
+    assert np.array_equal(pos, x) and np.array_equal(boxes[0], box)
+    assert steps.tolist() == [42] and times.tolist() == [8.5]
+
+
+def test_xtc_compressed_header_fields(tmp_path):
+    rng = np.random.default_rng(17)
+    x = _water_box(rng, 40, 3.0)[None]
+    path = tmp_path / "w.xtc"
+    XTCFile.write(path, x, [3.0, 3.0, 3.0], precision=1000.0)
+    blob = path.read_bytes()
+    natoms, precision = struct.unpack_from(">if", blob, 52)
+    minint = np.array(struct.unpack_from(">3i", blob, 60))
+    maxint = np.array(struct.unpack_from(">3i", blob, 72))
+    smallidx, nbytes = struct.unpack_from(">ii", blob, 84)
+    assert natoms == 120 and precision == 1000.0
+    ints = np.trunc(x[0].astype(np.float32) * np.float32(1000.0) + np.copysign(np.float32(0.5), x[0])).astype(int)
+    assert np.array_equal(minint, ints.min(axis=0)) and np.array_equal(maxint, ints.max(axis=0))
+    assert 9 <= smallidx < 73 and len(blob) == 92 + (nbytes + 3) // 4 * 4
+    # far fewer bits than 3 x 12 per atom: the run coding engaged
+    assert nbytes < 120 * 36 // 8
+
+
+@pytest.mark.parametrize("case", ["water", "gas", "huge", "tiny-spread", "ten"])
+def test_xtc_round_trip_and_independent_decoder(tmp_path, case):
+    rng = np.random.default_rng(23)
+    precision = 1000.0
+    if case == "water":
+        x = np.stack([_water_box(rng, 300, 4.0) for _ in range(4)])
+    elif case == "gas":  # no two consecutive atoms close: every atom takes the full-size code
+        x = rng.uniform(-6.0, 6.0, size=(3, 257, 3))
+    elif case == "huge":  # extent above 2^24 quanta: the per-component bit fields
+        x, precision = rng.uniform(-10.0, 10.0, size=(2, 100, 3)), 1.0e6
+    elif case == "tiny-spread":  # everything within a few quanta: smallest radix, long runs
+        x = 1.0 + rng.integers(0, 4, size=(2, 64, 3)) * 1e-3
+    else:  # the smallest compressed frame
+        x = rng.uniform(0.0, 2.0, size=(3, 10, 3))
+    frames = x.shape[0]
+    path = tmp_path / "t.xtc"
+    boxes = np.array([np.diag([4.0, 4.5, 5.0]) + 0.01 * b for b in range(frames)])
+    XTCFile.write(path, x, boxes, steps=np.arange(frames) * 500, times=np.arange(frames) * 1.0, precision=precision)
+    xtc = open_trajectory(path)
+    assert isinstance(xtc, XTCFile) and (len(xtc), xtc.numAtoms) == (frames, x.shape[1])
+    assert xtc.precision == np.float32(precision)
+    pos, box, steps, times = xtc.readFrames(0, frames)
+    # rounding to the grid: half a quantum plus float32 rounding of the product
+    assert np.abs(pos - x).max() <= 0.5 / precision + 2e-6 * np.abs(x).max()
+    assert np.allclose(box, boxes.astype(np.float32)) and steps.tolist() == (np.arange(frames) * 500).tolist()
+    # the independent reading of the same bytes
+    reference = xtc_python.read_frames(path)
+    assert len(reference) == frames
+    for b, (step, time, ref_box, xyz) in enumerate(reference):
+        assert step == steps[b] and time == times[b]
+        assert np.array_equal(ref_box, box[b].astype(np.float32))
+        assert np.array_equal(xyz, pos[b]), f"frame {b} differs from the reference decoder"
+    # decoded values sit exactly on the grid: a second round trip is lossless
+    again = tmp_path / "again.xtc"
+    XTCFile.write(again, pos, box, steps=steps, times=times, precision=precision)
+    second = XTCFile(again).readFrames(0, frames)[0]
+    if case == "huge":  # 1e7 quanta leave float32 one bit: the product can round to the neighbour
+        assert np.abs(second - pos).max() <= 1.5 / precision
+    else:
+        assert np.array_equal(second, pos)
+    # random access and threads
+    one = XTCFile(path, readThreads=1)
+    assert np.array_equal(one.read(frames - 1, 1)[0][0], pos[-1])
+    with pytest.raises(IndexError):
+        one.read(frames, 1)
+
+
+def test_xtc_append_truncation_and_foreign_files(tmp_path):
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 3, size=(4, 50, 3))
+    path = tmp_path / "a.xtc"
+    XTCFile.write(path, x[:2])
+    XTCFile.write(path, x[2:], append=True)
+    whole = XTCFile(path)
+    assert len(whole) == 4
+    pos, box = whole.read(0, 4)
+    assert box is None and np.abs(pos - x).max() <= 5.1e-4
+    # a writer killed mid-frame leaves a partial last frame: ignored
+    blob = path.read_bytes()
+    (tmp_path / "cut.xtc").write_bytes(blob[:-7])
+    assert len(XTCFile(tmp_path / "cut.xtc")) == 3
+    (tmp_path / "bad.xtc").write_bytes(b"\0" * 200)
+    with pytest.raises(Exception, match="not an XTC file"):
+        XTCFile(tmp_path / "bad.xtc")
+    other = tmp_path / "other.xtc"
+    XTCFile.write(other, x[:1, :20])
+    (tmp_path / "mixed.xtc").write_bytes(blob + other.read_bytes())
+    with pytest.raises(Exception, match="number of atoms changes"):
+        XTCFile(tmp_path / "mixed.xtc")
+    with pytest.raises(Exception, match="too large"):
+        XTCFile.write(tmp_path / "big.xtc", np.full((1, 12, 3), 3.0e6), precision=1000.0)
