@@ -167,21 +167,23 @@ def measured_peaks() -> dict:
 
 
 # ---- DRAM traffic from the committed ncu captures, valid only for the build that was profiled ----------
-def kernel_source_hash() -> str:
-    """Hash of the CUDA sources: a committed ncu capture speaks for this build only if it matches."""
+def kernel_source_hash(files=None) -> str:
+    """Hash of the CUDA sources a kernel is built from (all of csrc/ when `files` is None): a
+    committed ncu capture speaks for this build only if it matches."""
     digest = hashlib.sha256()
     base = os.path.join(ROOT, "cvpack_b200", "csrc")
-    for name in sorted(os.listdir(base)):
-        if name.endswith((".cu", ".cuh")):
-            with open(os.path.join(base, name), "rb") as file:
-                digest.update(name.encode() + b"\0" + file.read())
+    names = sorted(files) if files else sorted(n for n in os.listdir(base) if n.endswith((".cu", ".cuh")))
+    for name in names:
+        with open(os.path.join(base, name), "rb") as file:
+            digest.update(name.encode() + b"\0" + file.read())
     return digest.hexdigest()[:16]
 
 
 def ncu_traffic(kernel: str, frames_per_launch: float):
     """(bytes per launch or None, provenance).  profiles/traffic.json holds, per kernel, the
     dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, the frames of that
-    launch and the source hash of the build it profiled."""
+    launch, the source files of the kernel and their hash in the build that was profiled
+    (scripts/make_traffic.py writes it from the committed summaries)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path) or not frames_per_launch:
         return None, "no committed ncu capture"
@@ -190,9 +192,10 @@ def ncu_traffic(kernel: str, frames_per_launch: float):
     entry = table.get(kernel)
     if entry is None:
         return None, "no committed ncu capture for this kernel"
-    if entry.get("source_hash") != kernel_source_hash():
+    now = kernel_source_hash(entry.get("files"))
+    if entry.get("source_hash") != now:
         return None, (f"{entry['source']} profiled build {entry.get('source_hash')}, this build is "
-                      f"{kernel_source_hash()}: traffic not carried over")
+                      f"{now}: traffic not carried over")
     return entry["bytes"] / entry["frames"] * frames_per_launch, entry["source"]
 
 
@@ -496,9 +499,13 @@ def run_extras(device, sampler, steps, peaks, select=None) -> list:
         kernel_total = sum(v[0] for v in used.values())
         flop = frames * 2.0 * (2 * 9 * 64 * n)  # covariance + gradient contractions, FMA = 2
         achieved = steps_ * flop / (kernel_total * 1e-3) / 1e12 if kernel_total else None
+        # DRAM bytes of one covariance + one gradient launch (both see every frame of the step)
+        parts = [ncu_traffic(k, frames) for k in ("rmsd_multi_cov", "rmsd_multi_gradient")]
+        traffic = sum(p[0] for p in parts) if all(p[0] is not None for p in parts) else None
         return {
             "bound": "fp64", "kernel": "+".join(sorted(used)), "achieved": achieved, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": achieved / fp64_peak if achieved else None, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved / fp64_peak if achieved else None, "traffic": traffic,
+            "traffic_source": parts[0][1] + " (covariance + gradient launch)" if traffic else parts[0][1],
             "peak_source": "DFMA microbenchmark in this run (cvp_measure_fp64_peak)",
             "launches": sum(v[1] for v in used.values()),
             "kernel_share_of_step": kernel_total / (ms * steps_) if kernel_total else None,
