@@ -750,7 +750,11 @@ struct RmsdCV : cvp_cv {
   // many references over one contiguous atom set (rmsd_multi.cuh)
   bool multi = false;
   int use_multi = 1;  // option "multi"
-  int use_multi_mma = 1;  // option "multi_mma": FP64 tensor-core (DMMA) versions of the multi kernels
+  // option "multi_mma": FP64 tensor-core (DMMA) versions of the multi kernels; 1 = gradient operands
+  // pre-packed in fragment order and fed by TMA, 2 = register-staged gradient, 0 = SIMT DFMA
+  int use_multi_mma = 1;
+  std::vector<double> ref_pack;  // references in the fragment order of rmsd_multi_gradient_pk_kernel
+  DeviceBuffer d_ref_pack;
   int multi_first = 0, multi_n = 0, multi_sk_max = 1;
   std::vector<float> ref_f32;
   std::vector<int32_t> fast_seg_slice_offsets;
@@ -781,7 +785,7 @@ struct RmsdCV : cvp_cv {
          {&d_entry_atom, &d_entry_group, &d_entry_seg, &d_ref, &d_slices, &d_group_seg_offsets,
           &d_seg_slice_offsets, &d_seg_size, &d_group_size, &d_group_gy, &d_active,
           &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_ref_perm, &d_fast_seg_slice_offsets,
-          &d_entry_slot, &d_group_entry_offsets})
+          &d_entry_slot, &d_group_entry_offsets, &d_ref_pack})
       buf->release();
   }
   int upload() override {
@@ -806,6 +810,7 @@ struct RmsdCV : cvp_cv {
     CVP_UP(d_fast_seg_slice_offsets, fast_seg_slice_offsets);
     CVP_UP(d_entry_slot, entry_slot);
     CVP_UP(d_group_entry_offsets, group_entry_offsets);
+    CVP_UP(d_ref_pack, ref_pack);
 #undef CVP_UP
     return CVP_OK;
   }
@@ -813,10 +818,14 @@ struct RmsdCV : cvp_cv {
     // (the fused kernel's records only exist for the single contiguous group it serves)
     return (fast ? FusedLaunch<RmsdFusedPolicy>::workspace_per_frame((int)num_entries) : 0) +
            (size_t)std::max(nslice, fast_nslice) * 13 * sizeof(double) + (size_t)num_groups * sizeof(RmsdSolution) +
-           (size_t)nseg * 3 * sizeof(double) + (size_t)num_groups * sizeof(double) + 64;
+           (size_t)nseg * 3 * sizeof(double) + (size_t)num_groups * sizeof(double) + 64 + w_pack_bytes(1);
   }
   size_t workspace_fixed(int) const override {
-    return 6 * 256 + FusedLaunch<RmsdFusedPolicy>::workspace_fixed();
+    // (the packed W records are padded to whole tiles of MULTI_TF frames)
+    return 7 * 256 + FusedLaunch<RmsdFusedPolicy>::workspace_fixed() + w_pack_bytes(MULTI_TF);
+  }
+  size_t w_pack_bytes(int64_t frames) const {
+    return multi ? (size_t)frames * pk_stages(num_groups) * PK_KG * 9 * sizeof(double) : 0;
   }
   int set_option(const char* name, int value) override {
     const std::string key(name);
@@ -877,6 +886,8 @@ struct RmsdCV : cvp_cv {
     RmsdSolution* solution = carve.take<RmsdSolution>((size_t)B * num_groups);
     double* seg_centroid = carve.take<double>((size_t)B * nseg * 3);
     double* group_factor = carve.take<double>((size_t)B * num_groups);
+    double* w_pack = multi ? carve.take<double>(w_pack_bytes(div_up(B, MULTI_TF) * MULTI_TF) / sizeof(double))
+                           : nullptr;
 
     // streaming fast path: FP32, one contiguous aligned group
     const bool use_fast = fast && std::is_same<T, float>::value && (N % 4) == 0 &&
@@ -968,7 +979,31 @@ struct RmsdCV : cvp_cv {
         CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_gradient_mma_kernel,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)MULTI_GRAD_MMA_SMEM));
+        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_gradient_pk_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)MULTI_GRAD_PK_SMEM));
+        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_gradient_pk_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)MULTI_GRAD_PK_SMEM));
         multi_configured = true;
+      }
+      if (use_multi_mma == 1) {
+        const int64_t padded = div_up(B, MULTI_TF) * MULTI_TF * pk_stages(num_groups) * PK_KG;
+        rmsd_multi_weights_pack_kernel<RmsdSolution><<<(unsigned)div_up(padded, 256), 256, 0, st>>>(
+            solution, group_factor, B, num_groups, w_pack);
+        CVP_LAUNCH_CHECK();
+        // whole rows of the tiles as bulk copies when every row starts and ends on 16 bytes
+        const bool bulk = multi_first % 4 == 0 && N % 4 == 0 && multi_n % 4 == 0 &&
+                          ((reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0;
+        auto kernel = bulk ? rmsd_multi_gradient_pk_kernel<true> : rmsd_multi_gradient_pk_kernel<false>;
+        timer.begin("rmsd_multi_gradient", st);
+        kernel<<<grad_grid, MULTI_THREADS, MULTI_GRAD_PK_SMEM, st>>>(
+            reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+            static_cast<const double*>(d_ref_pack.ptr), num_groups, B, w_pack, group_factor,
+            seg_centroid, nseg, reinterpret_cast<float*>(grad), accumulate ? 1 : 0);
+        timer.end(st);
+        CVP_LAUNCH_CHECK();
+        return CVP_OK;
       }
       // the slice records are dead after the solve: their memory holds the W = factor * U^T records
       double* weights = partials;
@@ -1228,6 +1263,7 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
       // slices over the atoms: at least 512 atoms each, never more than the generic path reserves
       // workspace for (ceil(n / 1024) per group)
       cv->multi_sk_max = (int)std::max<int64_t>(1, std::min<int64_t>({16, n / 512, div_up(n, 1024)}));
+      pk_pack_reference(cv->ref.data(), G, (int)n, cv->ref_pack);
     }
   }
   *out = cv;

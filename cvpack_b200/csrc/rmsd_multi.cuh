@@ -669,6 +669,238 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
   }
 }
 
+// ---- gradient, operands pre-packed in fragment order and fed by TMA ---------------------------------
+// The register-staged kernel above reaches 60 % of the DMMA issue rate: K = 3 G is short, a stage
+// holds 36 DMMA per warp, and the global loads of the next stage (scattered 8-byte loads with
+// per-thread index tables, 24 registers) come back later than that.  Both operands are constants
+// of something larger than a CTA -- the reference of the whole spec, the W records of a batch --
+// so they are written ONCE in the order the fragments are read:
+//   ref_pack [atom tile][stage][k-step][8 column tiles][32]   (host, at upload; zero padded)
+//   w_pack   [frame tile][stage][k-step][12 row tiles][32]    (rmsd_multi_weights_pack_kernel)
+// A stage of either is one contiguous block: one elected thread moves it with cp.async.bulk into a
+// ring of PK_STAGES slots (full / empty mbarriers), no thread spends a register or an instruction
+// on operand loads, and the main loop is LDS.64 + DMMA only.
+#ifndef PK_KG_VALUE
+#define PK_KG_VALUE 4
+#endif
+#ifndef PK_STAGES_VALUE
+#define PK_STAGES_VALUE 4
+#endif
+constexpr int PK_KG = PK_KG_VALUE;            // groups per stage (3 PK_KG must be a multiple of 4)
+constexpr int PK_STAGES = PK_STAGES_VALUE;    // ring slots
+constexpr int PK_KS = PK_KG * 3 / 4;          // k-steps per stage
+constexpr int PK_A_STAGE = PK_KS * (MMA_ROWS / 8) * 32;  // doubles
+constexpr int PK_B_STAGE = PK_KS * (MMA_TA / 8) * 32;
+static_assert(PK_KG * 3 % 4 == 0, "a stage is a whole number of k-steps");
+constexpr size_t MULTI_GRAD_PK_SMEM = PK_STAGES * sizeof(double) * (PK_A_STAGE + PK_B_STAGE) +
+                                      sizeof(float) * MULTI_TF * MMA_X_PITCH + sizeof(double) * MULTI_TF * 4 +
+                                      2 * PK_STAGES * sizeof(uint64_t);
+
+inline int pk_stages(int num_groups) { return (num_groups + PK_KG - 1) / PK_KG; }
+// position of B[k = 3 gl + d][column = al] of a stage / A[row = 3 fl + c][k] in its block
+__host__ __device__ inline int pk_b_index(int gl, int d, int al) {
+  const int kk = 3 * gl + d;
+  return (((kk >> 2) * (MMA_TA / 8) + (al >> 3)) << 5) + ((al & 7) << 2) + (kk & 3);
+}
+__host__ __device__ inline int pk_a_index(int gl, int d, int fl, int c) {
+  const int kk = 3 * gl + d, r = 3 * fl + c;
+  return (((kk >> 2) * (MMA_ROWS / 8) + (r >> 3)) << 5) + ((r & 7) << 2) + (kk & 3);
+}
+
+// host: the centred references [G][n][3] -> ref_pack
+inline void pk_pack_reference(const double* ref, int num_groups, int n, std::vector<double>& out) {
+  const int tiles = (n + MMA_TA - 1) / MMA_TA, ns = pk_stages(num_groups);
+  out.assign((size_t)tiles * ns * PK_B_STAGE, 0.0);
+  for (int g = 0; g < num_groups; ++g) {
+    const int s = g / PK_KG, gl = g % PK_KG;
+    for (int a = 0; a < n; ++a) {
+      double* block = out.data() + ((size_t)(a / MMA_TA) * ns + s) * PK_B_STAGE;
+      for (int d = 0; d < 3; ++d) block[pk_b_index(gl, d, a % MMA_TA)] = ref[((size_t)g * n + a) * 3 + d];
+    }
+  }
+}
+
+// W[f][g][3c+d] = factor[f][g] U^T[f][g][3c+d] -> w_pack; one thread per (padded frame, padded group)
+template <typename Solution>
+__global__ void rmsd_multi_weights_pack_kernel(const Solution* __restrict__ solution,
+                                               const double* __restrict__ factor, int64_t num_frames,
+                                               int num_groups, double* __restrict__ w_pack) {
+  const int ns = (num_groups + PK_KG - 1) / PK_KG, gp = ns * PK_KG;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t frames_pad = (num_frames + MULTI_TF - 1) / MULTI_TF * MULTI_TF;
+  if (t >= frames_pad * gp) return;
+  const int64_t f = t / gp;
+  const int g = (int)(t - f * gp);
+  const bool real = f < num_frames && g < num_groups;
+  const double fac = real ? factor[f * num_groups + g] : 0.0;
+  const double* ut = solution[real ? f * num_groups + g : 0].ut;
+  double* block = w_pack + ((f / MULTI_TF) * ns + g / PK_KG) * PK_A_STAGE;
+  const int fl = (int)(f % MULTI_TF), gl = g % PK_KG;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) block[pk_a_index(gl, d, fl, c)] = real ? fac * ut[3 * c + d] : 0.0;
+}
+
+// grid = (frame tiles, atom tiles), MULTI_THREADS threads, dynamic shared memory MULTI_GRAD_PK_SMEM.
+// BULK (positions and gradient 16-byte aligned, first_atom, N and n multiples of 4): the x tile comes
+// in and the gradient tile goes out as one bulk copy per frame row (768 bytes), issued by the lanes
+// of warp 0 -- in the scalar version the index arithmetic of those two loops was 70 % of the
+// kernel's instructions (ncu source page, round 2).
+template <bool BULK>
+__global__ void __launch_bounds__(MULTI_THREADS, 2)
+    rmsd_multi_gradient_pk_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom, int n,
+                                  const double* __restrict__ ref_pack, int num_groups, int64_t num_frames,
+                                  const double* __restrict__ w_pack, const double* __restrict__ factor,
+                                  const double* __restrict__ centroid /* [frame][nseg][3], seg 0 */,
+                                  int nseg, float* __restrict__ grad, int accumulate) {
+  extern __shared__ __align__(16) double multi_smem[];
+  double* ring = multi_smem;  // [PK_STAGES][A stage | B stage]
+  float* xs = reinterpret_cast<float*>(ring + PK_STAGES * (PK_A_STAGE + PK_B_STAGE));  // [32][MMA_X_PITCH]
+  double* fc = reinterpret_cast<double*>(xs + MULTI_TF * MMA_X_PITCH);                  // [32][4]: c_f, F_f
+  uint64_t* full = reinterpret_cast<uint64_t*>(fc + MULTI_TF * 4);
+  uint64_t* empty = full + PK_STAGES;
+  __shared__ __align__(8) uint64_t xbar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int64_t f0 = (int64_t)blockIdx.x * MULTI_TF;
+  const int a0 = blockIdx.y * MMA_TA;
+  const int atoms_here = min(MMA_TA, n - a0);
+  const int frames_here = (int)min((int64_t)MULTI_TF, num_frames - f0);
+  const int ns = (num_groups + PK_KG - 1) / PK_KG;
+  const double* a_src = w_pack + (size_t)blockIdx.x * ns * PK_A_STAGE;
+  const double* b_src = ref_pack + (size_t)blockIdx.y * ns * PK_B_STAGE;
+  constexpr uint32_t STAGE_BYTES = (PK_A_STAGE + PK_B_STAGE) * sizeof(double);
+
+  auto issue = [&](int s) {  // one thread: stage s -> slot s % PK_STAGES
+    const int slot = s % PK_STAGES;
+    double* dst = ring + (size_t)slot * (PK_A_STAGE + PK_B_STAGE);
+    mbar_expect_tx(&full[slot], STAGE_BYTES);
+    tma_load_1d(dst, a_src + (size_t)s * PK_A_STAGE, PK_A_STAGE * sizeof(double), &full[slot]);
+    tma_load_1d(dst + PK_A_STAGE, b_src + (size_t)s * PK_B_STAGE, PK_B_STAGE * sizeof(double), &full[slot]);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < PK_STAGES; ++k) {
+      mbar_init(&full[k], 1);
+      mbar_init(&empty[k], MULTI_THREADS / 32);
+    }
+    if (BULK) mbar_init(&xbar, 1);
+    mbar_fence_init();
+    for (int s = 0; s < min(ns, PK_STAGES); ++s) issue(s);
+    if (BULK) mbar_expect_tx(&xbar, (uint32_t)(frames_here * atoms_here * 12));
+  }
+
+  // x tile and the frame constants, consumed by the epilogue -- under the first copies
+  if (BULK) {
+    // (rows of frames past the batch and columns past the group stay undefined: never stored)
+    __syncthreads();  // xbar initialised and armed
+    if (warp == 0 && lane < frames_here)
+      tma_load_1d(xs + lane * MMA_X_PITCH, pos + ((f0 + lane) * num_atoms + first_atom + a0) * 3,
+                  (uint32_t)(atoms_here * 12), &xbar);
+  } else {
+    for (int e = tid; e < MULTI_TF * MMA_TA * 3; e += MULTI_THREADS) {
+      const int fl = e / (MMA_TA * 3), rest = e - fl * (MMA_TA * 3);
+      float v = 0.f;
+      if (f0 + fl < num_frames && rest < atoms_here * 3)
+        v = pos[((f0 + fl) * num_atoms + first_atom + a0) * 3 + rest];
+      xs[fl * MMA_X_PITCH + rest] = v;
+    }
+  }
+  {
+    // F_f = sum_g factor[f][g]: 8 threads per frame, each a strided eighth of the groups
+    const int fl = tid >> 3, part = tid & 7;
+    const int64_t f = f0 + fl;
+    double sum = 0.0;
+    if (f < num_frames)
+      for (int g = part; g < num_groups; g += 8) sum += __ldg(factor + f * num_groups + g);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    if (part < 4) {
+      double v = sum;
+      if (part < 3) v = f < num_frames ? centroid[(size_t)f * nseg * 3 + part] : 0.0;
+      fc[4 * fl + part] = v;
+    }
+  }
+  __syncthreads();  // barriers initialised, x tile and constants in place
+
+  double acc[3][4][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int s = 0; s < ns; ++s) {
+    const int slot = s % PK_STAGES;
+    const uint32_t parity = (uint32_t)(s / PK_STAGES) & 1u;
+    mbar_wait(&full[slot], parity);
+    const double* as = ring + (size_t)slot * (PK_A_STAGE + PK_B_STAGE);
+    const double* bs = as + PK_A_STAGE;
+#pragma unroll
+    for (int ks = 0; ks < PK_KS; ++ks) {
+      double a[3], b[4];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) a[i] = as[((ks * (MMA_ROWS / 8) + 3 * wm + i) << 5) + lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = bs[((ks * (MMA_TA / 8) + 4 * wn + j) << 5) + lane];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
+    }
+    if (s + PK_STAGES < ns) {  // the slot is refilled once every warp has read it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+      if (tid == 0) {
+        mbar_wait(&empty[slot], parity);
+        issue(s + PK_STAGES);
+      }
+    }
+  }
+  // epilogue: v = F (x - c) - acc in double, written over x in the shared tile, then whole rows
+  if (BULK) mbar_wait(&xbar, 0);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int r = 8 * (3 * wm + i) + (lane >> 2);
+    const int fl = r / 3, c = r - 3 * fl;
+    const double cf = fc[4 * fl + c], big_f = fc[4 * fl + 3];
+    float* row = xs + fl * MMA_X_PITCH + (8 * 4 * wn + 2 * (lane & 3)) * 3 + c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float* slot = row + (8 * j + h) * 3;
+        *slot = (float)(big_f * ((double)*slot - cf) - acc[i][j][h]);
+      }
+    }
+  }
+  if (BULK) {
+    fence_proxy_async_smem();  // the generic-proxy writes above are read by the bulk stores below
+    __syncthreads();
+    if (warp == 0) {
+      if (lane < frames_here) {
+        float* out = grad + ((f0 + lane) * num_atoms + first_atom + a0) * 3;
+        if (accumulate)
+          tma_reduce_add_f32_1d(out, xs + lane * MMA_X_PITCH, (uint32_t)(atoms_here * 12));
+        else
+          tma_store_1d(out, xs + lane * MMA_X_PITCH, (uint32_t)(atoms_here * 12), l2_policy_evict_first());
+      }
+      tma_commit_group();
+      tma_wait_group_read<0>();  // the tile must outlive the reads
+    }
+    return;
+  }
+  __syncthreads();
+  for (int e = tid; e < MULTI_TF * MMA_TA * 3; e += MULTI_THREADS) {
+    const int fl = e / (MMA_TA * 3), rest = e - fl * (MMA_TA * 3);
+    if (f0 + fl >= num_frames || rest >= atoms_here * 3) continue;
+    float* out = grad + ((f0 + fl) * num_atoms + first_atom + a0) * 3 + rest;
+    const float v = xs[fl * MMA_X_PITCH + rest];
+    *out = accumulate ? *out + v : v;
+  }
+}
+
 constexpr size_t MULTI_GRAD_SMEM =
     2 * sizeof(double) * (MULTI_KG * MULTI_TF * 10 + MULTI_KG * MULTI_TA * 3);
 

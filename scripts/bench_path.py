@@ -21,7 +21,7 @@ value = torch.empty(frames, device=device)
 grad = torch.empty((frames, 20000, 3), device=device)
 from cvpack_b200 import _native  # noqa: E402
 print(json.dumps({"fp64_dfma_peak_tflops": _native.measure_fp64_peak(0), "fp32_ffma_peak_tflops": _native.measure_fp32_peak(0)}))
-for mma in (1, 0):
+for mma in (1, 2, 0):
     native.set_option("multi_mma", mma)
     for _ in range(2):
         ctx.evaluateInto(cv, value, grad)

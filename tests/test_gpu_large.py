@@ -275,16 +275,18 @@ def test_symmetric_sweep_vs_c_oracle(periodic):
 
 @pytest.mark.parametrize("metric", ["progress", "deviation"])
 @pytest.mark.parametrize(
-    "n_group,first,frames,milestones",
-    # (odd atom counts take the 8-byte copies of the gradient kernel, 129 = one atom past a tile)
-    [(300, 8, 70, 5), (1000, 0, 33, 37), (129, 3, 40, 9), (257, 0, 65, 3)],
+    "n_group,first,frames,milestones,tail",
+    # (129 = one atom past a tile; the last two shapes have every row of a tile on 16-byte
+    # boundaries and take the bulk-copy rows of the gradient kernel, 296 = 4 tiles + 40 atoms)
+    [(300, 8, 70, 5, 5), (1000, 0, 33, 37, 5), (129, 3, 40, 9, 5), (257, 0, 65, 3, 5), (296, 8, 70, 5, 4),
+     (128, 4, 33, 9, 0)],
 )
-def test_path_many_references_one_atom_set(metric, n_group, first, frames, milestones):
+def test_path_many_references_one_atom_set(metric, n_group, first, frames, milestones, tail):
     """PathInRMSDSpace whose milestones all list the same contiguous atoms takes the tiled
     double-precision contractions of rmsd_multi.cuh: against the NumPy oracle and against the
     generic per-entry kernels."""
     rng = np.random.default_rng(37)
-    n = first + n_group + 5
+    n = first + n_group + tail
     system = helpers.make_system(n, rng)
     start, end = rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
     atoms = list(range(first, first + n_group))
@@ -311,14 +313,32 @@ def test_path_many_references_one_atom_set(metric, n_group, first, frames, miles
     # replace must agree to the rounding of a different summation order
     assert native.set_option("multi_mma", 0) == 1
     value3, grad3 = cv.getValueAndGradient(ctx)
-    native.set_option("multi_mma", 1)
     assert torch.allclose(value3._value, value._value, rtol=1e-6, atol=1e-7)
     assert (grad3 - grad).abs().max() <= 1e-6 * grad.abs().max()
+    # ... and the register-staged DMMA gradient sums in the same order as the TMA-fed default
+    native.set_option("multi_mma", 2)
+    value5, grad5 = cv.getValueAndGradient(ctx)
+    native.set_option("multi_mma", 1)
+    assert torch.equal(value5._value, value._value) and torch.equal(grad5, grad)
     value4, grad4 = cv.getValueAndGradient(ctx)
     assert torch.equal(value4._value, value._value) and torch.equal(grad4, grad), "not deterministic"
     outside = torch.ones(n, dtype=torch.bool)
     outside[atoms] = False
     assert not grad[:, outside].any()
+    # CVP_FLAG_ACCUMULATE through the raw C ABI: value and gradient are added to what is there
+    from cvpack_b200 import _native  # pylint: disable=import-outside-toplevel
+
+    pos = ctx.getPositions()
+    base_value = torch.full_like(value._value, 0.25)
+    base_grad = torch.full_like(grad, -0.5)
+    acc_value, acc_grad = base_value.clone(), base_grad.clone()
+    native.evaluate(_native.CVP_F32, pos.data_ptr(), None, _native.CVP_BOX_NONE, frames, n, acc_value.data_ptr(),
+                    acc_grad.data_ptr(), _native.CVP_FLAG_ACCUMULATE, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.allclose(acc_value, base_value + value._value, rtol=1e-6, atol=1e-7)
+    expected = base_grad + grad
+    expected[:, outside] = -0.5
+    assert torch.equal(acc_grad, expected)
 
 
 @pytest.mark.parametrize("frames", [4, 80])
