@@ -43,7 +43,17 @@ constexpr int CELL_MAX_CELLS = CELL_MAX_AXIS * CELL_MAX_AXIS * CELL_MAX_AXIS;
 #endif
 constexpr int CELL_SWEEP_THREADS = CELL_SWEEP_THREADS_VALUE;
 constexpr int CELL_SMEM_BUDGET = 64 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
-constexpr int CELL_SMEM_BUDGET_SYM = 72 * 1024;  // ... with the j gradient accumulators
+// Phase 2 of the sweep (SWEEP_P2): 0 = hit masks in registers, stage and accumulators through
+// generic pointers (round-2 start); 1 = hit masks in a per-warp shared array (a lane that runs out of
+// bits fetches its next word with one load instead of a select chain over four registers) and
+// explicit 32-bit shared addresses for the staged atom and the j accumulators
+#ifndef SWEEP_P2
+#define SWEEP_P2 1
+#endif
+#ifndef CELL_SMEM_BUDGET_SYM_KB
+#define CELL_SMEM_BUDGET_SYM_KB (SWEEP_P2 ? 63 : 72)
+#endif
+constexpr int CELL_SMEM_BUDGET_SYM = CELL_SMEM_BUDGET_SYM_KB * 1024;  // ... with the j gradient accumulators
 constexpr int TAG_DUMMY = -1;
 
 __host__ __device__ inline int cell_round_up(int n, int m) { return (n + m - 1) / m * m; }
@@ -316,7 +326,8 @@ __host__ __device__ inline size_t cell_sweep_smem(bool sym = false) {
   return sizeof(T4) * ((size_t)jchunk + (size_t)(jchunk / CELL_CLUSTER) * 2 +
                        (size_t)(CELL_SWEEP_THREADS / 32) * batch_atoms) +
          (size_t)(CELL_SWEEP_THREADS / 32) * SURV_CAP * sizeof(uint16_t) +
-         (sym ? (size_t)jchunk * 4 * sizeof(int) : 0);
+         (sym ? (size_t)jchunk * 4 * sizeof(int) : 0) +
+         (SWEEP_P2 ? (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms / 32) * 32 * sizeof(uint32_t) : 0);
 }
 
 // Symmetric mode: exact fixed-point accumulation.  x = round(v * scale) (F2I, |v * scale| < 2^30 by
@@ -356,6 +367,35 @@ __device__ __forceinline__ void sym_add3(int* lo, int* wraps, float vx, float vy
     atomicAdd(wraps, bump);
   }
 #endif
+}
+// the same through 32-bit shared-window addresses (acc = &lo[0], wraps = &wrap word)
+__device__ __forceinline__ unsigned atoms_add(uint32_t addr, unsigned x) {
+  unsigned old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(x) : "memory");
+  return old;
+}
+__device__ __forceinline__ void sym_add3_s(uint32_t acc, uint32_t jacc_s, uint32_t jwrap_s, float vx, float vy, float vz, float scale) {
+  const unsigned x0 = sym_fixed(vx, scale), x1 = sym_fixed(vy, scale), x2 = sym_fixed(vz, scale);
+  const unsigned o0 = atoms_add(acc, x0), o1 = atoms_add(acc + 4, x1), o2 = atoms_add(acc + 8, x2);
+  const unsigned n0 = o0 + x0, n1 = o1 + x1, n2 = o2 + x2;
+  const unsigned f0 = (o0 ^ n0) & (x0 ^ n0), f1 = (o1 ^ n1) & (x1 ^ n1), f2 = (o2 ^ n2) & (x2 ^ n2);
+  if ((int)(f0 | f1 | f2) < 0) {
+    int bump = 0;
+    if ((int)f0 < 0) bump += (int)x0 < 0 ? -1 : 1;
+    if ((int)f1 < 0) bump += ((int)x1 < 0 ? -1 : 1) << 10;
+    if ((int)f2 < 0) bump += ((int)x2 < 0 ? -1 : 1) << 20;
+    atoms_add(jwrap_s + (acc - jacc_s) / 12u * 4u, (unsigned)bump);
+  }
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ float sym_value(int lo, int wraps, int component, float inv_scale) {
   const int carry = ((wraps >> (10 * component)) & 1023) - 512;
@@ -397,7 +437,8 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   T4* bsm = jsm + jchunk;  // cluster boxes of the chunk: (centre, half) pairs
   T4* stage_all = bsm + (jchunk / CELL_CLUSTER) * 2;       // [NWARP][BATCH_ATOMS]
   T4* survivors_all = stage_all + NWARP * BATCH_ATOMS;    // [NWARP][SURV_CAP] 16-bit entries
-  int* jacc = reinterpret_cast<int*>(reinterpret_cast<uint16_t*>(survivors_all) + NWARP * SURV_CAP);  // SYM: [jchunk][3] wrapping sums
+  uint32_t* hits_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(survivors_all) + NWARP * SURV_CAP);  // SWEEP_P2: [NWARP][NW][32]
+  int* jacc = reinterpret_cast<int*>(hits_all + (SWEEP_P2 ? NWARP * NW * 32 : 0));  // SYM: [jchunk][3] wrapping sums
   int* jwrap = jacc + 3 * jchunk;                                  // SYM: [jchunk] packed wrap counters
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -558,16 +599,39 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
       // every batch (a batch of 16 *consecutive* clusters lies on one side of the tile: the lanes
       // on that side had 2.3 x the average number of hits, ncu: 14 of 32 lanes active).
       T4* stg = stage_all + warp * BATCH_ATOMS;
+#if SWEEP_P2
+      const uint32_t stg_s = smem_addr(stg);
+      const uint32_t jacc_s = smem_addr(jacc), jwrap_s = smem_addr(jwrap);
+#endif
+#if SWEEP_P2
+      // batches of whole hit words (4 clusters = 32 staged atoms): `nq` words over `nb` batches, qmin
+      // or qmin + 1 each, so that phase 1 tests no word of padding.  Cluster e of batch b is survivor
+      // b + e nb while e < 4 qmin (the strided sample); the clusters of the extra word of the first
+      // `nq - qmin nb` batches come from the end of the list.
+      const int nq = (nsurv + 3) >> 2;
+      const int nb = (nq + NW - 1) / NW;
+      const int qmin = nb > 0 ? nq / nb : 0;
+      const int strided = 4 * qmin * nb;
+#else
       const int nb = (nsurv + BATCH_CL - 1) / BATCH_CL;
+#endif
       for (int bi = 0; bi < nb; ++bi) {
+#if SWEEP_P2
+        const int words = qmin + (bi < nq - qmin * nb ? 1 : 0);  // <= NW
+        const int take = 4 * words;                               // clusters, padding included
+        auto survivor = [&](int e) { return e < 4 * qmin ? bi + e * nb : strided + 4 * bi + (e - 4 * qmin); };
+#else
         const int take = (nsurv - bi + nb - 1) / nb;  // <= BATCH_CL
+        auto survivor = [&](int e) { return bi + e * nb; };
+#endif
         bool unsafe = false;
-        for (int a = lane; a < BATCH_ATOMS; a += 32) {
+        // (words that phase 1 does not test need no padding)
+        for (int a = lane; a < (SWEEP_P2 ? take * CELL_CLUSTER : BATCH_ATOMS); a += 32) {
           T4 pj;
           pj.x = pj.y = pj.z = T(1e18);  // padding of a short batch: never in range
           pj.w = tag_encode(TAG_DUMMY, T(0));
-          if (a < take * CELL_CLUSTER) {
-            const uint32_t ent = lst[bi + (a >> 3) * nb];
+          if (a < take * CELL_CLUSTER && survivor(a >> 3) < nsurv) {
+            const uint32_t ent = lst[survivor(a >> 3)];
             const int cl = (int)(ent & 0xffu);
             pj = jsm[cl * CELL_CLUSTER + (a & 7)];
             if (PBC == 1) {
@@ -589,8 +653,15 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               }
               unsafe |= (ent & SURV_UNSAFE) != 0u;
             }
-            if (SYM)  // the accumulator slot of the atom within the chunk (-1: padding)
+            if (SYM) {
+#if SWEEP_P2
+              // the shared-window address of the atom's accumulators (-1: padding)
+              pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : (int)(jacc_s + (uint32_t)(cl * CELL_CLUSTER + (a & 7)) * 12u), T(0));
+#else
+              // the accumulator slot of the atom within the chunk (-1: padding)
               pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : cl * CELL_CLUSTER + (a & 7), T(0));
+#endif
+            }
           }
           stg[a] = pj;
         }
@@ -616,7 +687,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           Acc e[NCH];
           T coef;
           if constexpr (FAST6) {
-            contacts_rational6(pc, r2, e[0], coef);
+            contacts_rational6<T, SYM && SWEEP_P2>(pc, r2, e[0], coef);
           } else if constexpr (KIND == CVP_PAIR_SOFTMIN) {
             Fn::eval_d(pc, ex[0], ex[1], ex[2], fc, e, coef);
           } else {
@@ -632,14 +703,20 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             gx -= fx;
             gy -= fy;
             gz -= fz;
-            if (SYM) sym_add3(jacc + tagj * 3, jwrap + tagj, (float)fx, (float)fy, (float)fz, sym_scale);
+            if constexpr (SYM) {
+#if SWEEP_P2
+              sym_add3_s((uint32_t)tagj, jacc_s, jwrap_s, (float)fx, (float)fy, (float)fz, sym_scale);
+#else
+              sym_add3(jacc + tagj * 3, jwrap + tagj, (float)fx, (float)fy, (float)fz, sym_scale);
+#endif
+            }
           }
         };
 
         // exact displacement of staged atom `slot` from the lane's atom: stored coordinates and the
         // image count of its cluster, in double (only instantiated for ShortestDistance)
         auto exact_displacement = [&](int slot, double (&ex)[3]) {
-          const uint32_t ent = lst[bi + (slot >> 3) * nb];
+          const uint32_t ent = lst[survivor(slot >> 3)];
           const T4 raw = jsm[(int)(ent & 0xffu) * CELL_CLUSTER + (slot & 7)];
           const uint32_t kx = (ent >> 8) & 3u, ky = (ent >> 10) & 3u, kz = (ent >> 12) & 3u;
           ex[0] = (double)raw.x - (double)pi.x - (kx == 1u ? (double)bx.ax : (kx == 2u ? -(double)bx.ax : 0.0));
@@ -667,6 +744,57 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           }
         } else {
           // phase 1: bit positions are compile-time constants
+#if SWEEP_P2
+          uint32_t* hw = hits_all + warp * (NW * 32) + lane;  // word w of this lane at hw[32 w]
+          int mine = 0;
+          // its 32-bit shared address, kept opaque so that it lives in a register instead of being
+          // recomputed from the thread index in the (divergent) refill path
+          uint32_t hw_s = smem_addr(hw);
+          asm volatile("" : "+r"(hw_s));
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            uint32_t m = 0u;
+            if (w < words) {  // warp-uniform
+#pragma unroll
+              for (int u = 0; u < 32; ++u) {
+                const T4 pj = stg[w * 32 + u];
+                const T dx = pj.x - pr.x, dy = pj.y - pr.y, dz = pj.z - pr.z;
+                if (fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2) m |= 1u << u;
+              }
+            }
+            hw[32 * w] = m;
+            mine += __popc(m);
+          }
+          const int rounds = __reduce_max_sync(FULL, mine);
+          // phase 2: every lane walks its own hit bits through a working copy `cur` of one mask
+          // word and reads its next word back from shared memory when `cur` runs out (same thread
+          // wrote it: no barrier).  Lanes start at different words, so that neighbouring i atoms
+          // (similar hit lists) do not reach the same j accumulator in the same instruction.
+          static_assert((NW & (NW - 1)) == 0, "NW must be a power of two");
+          int wsel = lane & (NW - 1);
+          uint32_t cur = hw[32 * wsel];
+          for (int it = 0; it < rounds; ++it) {
+            if (it < mine) {
+              while (cur == 0u) {
+                wsel = (wsel + 1) & (NW - 1);
+                cur = lds_u32(hw_s + 128u * (uint32_t)wsel);
+              }
+              const int k = wsel * 32 + __ffs(cur) - 1;
+              cur &= cur - 1u;
+              double ex[3] = {0.0, 0.0, 0.0};
+              if constexpr (KIND == CVP_PAIR_SOFTMIN) exact_displacement(k, ex);
+              if constexpr (sizeof(T) == 4) {
+                const float4 pj = lds_f4(stg_s + (uint32_t)k * 16u);
+                T4 pjt;
+                pjt.x = pj.x, pjt.y = pj.y, pjt.z = pj.z, pjt.w = pj.w;
+                interact(pjt, pjt.x - pr.x, pjt.y - pr.y, pjt.z - pr.z, false, ex);
+              } else {
+                const T4 pj = stg[k];
+                interact(pj, pj.x - pr.x, pj.y - pr.y, pj.z - pr.z, false, ex);
+              }
+            }
+          }
+#else
           uint32_t hits[NW];
 #pragma unroll
           for (int w = 0; w < NW; ++w) {
@@ -711,6 +839,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               interact(pj, pj.x - pr.x, pj.y - pr.y, pj.z - pr.z, false, ex);
             }
           }
+#endif
         }
         __syncwarp();  // the staging buffer is rewritten by the next batch
       }

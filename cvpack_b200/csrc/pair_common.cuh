@@ -83,7 +83,9 @@ __device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
 
 // NumberOfContacts with the default step function 1/(1+x^6): everything but the switching needs
 // only r^2 (x^6 = (r^2/r0^2)^3); branch-free switching.
-template <typename T>
+// SWITCH_ALWAYS: evaluate the switching polynomial unconditionally -- without a switching function
+// the host sets rs = 1/(rc - rs) = 0, so t = 0, sw = 1, dsw = 0 and the result is bitwise the same
+template <typename T, bool SWITCH_ALWAYS = false>
 __device__ __forceinline__ void contacts_rational6(const PairConsts<T>& pc, T r2, T& e, T& coef) {
   // r2 == 0 (coincident atoms): S(0) = 1 and no force, like the reference; avoids 0 * inf
   const T inv_r = r2 > T(0) ? fast_rsqrt(r2) : T(0);
@@ -93,7 +95,7 @@ __device__ __forceinline__ void contacts_rational6(const PairConsts<T>& pc, T r2
   const T inv_r2 = inv_r * inv_r;
   T c = T(-6) * x6 * s * s * inv_r2;  // (dS/dr)/r
   T en = s;
-  if (pc.has_switch) {
+  if (SWITCH_ALWAYS || pc.has_switch) {
     // sw = 1 - t^3 (10 - 15 t + 6 t^2),  dsw/dr = -30 t^2 (1 - t)^2 / (rc - rs),  t clamped at 0
     const T r = r2 * inv_r;
     const T t = fmax((r - pc.rs) * pc.inv_range, T(0));

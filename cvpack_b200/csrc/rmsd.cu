@@ -754,7 +754,8 @@ struct RmsdCV : cvp_cv {
   // pre-packed in fragment order and fed by TMA, 2 = register-staged gradient, 0 = SIMT DFMA
   int use_multi_mma = 1;
   std::vector<double> ref_pack;  // references in the fragment order of rmsd_multi_gradient_pk_kernel
-  DeviceBuffer d_ref_pack;
+  std::vector<double> ref_pack_cov;  // ... and of rmsd_multi_cov_pk_kernel
+  DeviceBuffer d_ref_pack, d_ref_pack_cov;
   int multi_first = 0, multi_n = 0, multi_sk_max = 1;
   std::vector<float> ref_f32;
   std::vector<int32_t> fast_seg_slice_offsets;
@@ -785,7 +786,7 @@ struct RmsdCV : cvp_cv {
          {&d_entry_atom, &d_entry_group, &d_entry_seg, &d_ref, &d_slices, &d_group_seg_offsets,
           &d_seg_slice_offsets, &d_seg_size, &d_group_size, &d_group_gy, &d_active,
           &d_atom_entry_offsets, &d_atom_entries, &d_ref_f32, &d_ref_perm, &d_fast_seg_slice_offsets,
-          &d_entry_slot, &d_group_entry_offsets, &d_ref_pack})
+          &d_entry_slot, &d_group_entry_offsets, &d_ref_pack, &d_ref_pack_cov})
       buf->release();
   }
   int upload() override {
@@ -811,6 +812,7 @@ struct RmsdCV : cvp_cv {
     CVP_UP(d_entry_slot, entry_slot);
     CVP_UP(d_group_entry_offsets, group_entry_offsets);
     CVP_UP(d_ref_pack, ref_pack);
+    CVP_UP(d_ref_pack_cov, ref_pack_cov);
 #undef CVP_UP
     return CVP_OK;
   }
@@ -941,8 +943,21 @@ struct RmsdCV : cvp_cv {
       const int ns_multi = num_groups * multi_sk;
       const dim3 cov_grid((unsigned)div_up(B, MULTI_TF), (unsigned)div_up(num_groups, MULTI_TG),
                           (unsigned)multi_sk);
+      // whole rows of the tiles as bulk copies when every row starts and ends on 16 bytes
+      const bool bulk_rows = multi_first % 4 == 0 && N % 4 == 0 && multi_n % 4 == 0 &&
+                             (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
+      static bool cov_configured = false;
+      if (!cov_configured) {
+        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_cov_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)MULTI_COV_PK_SMEM));
+        cov_configured = true;
+      }
       timer.begin("rmsd_multi_cov", st);
-      if (use_multi_mma)
+      if (use_multi_mma == 1 && bulk_rows)
+        rmsd_multi_cov_pk_kernel<<<cov_grid, MULTI_THREADS, MULTI_COV_PK_SMEM, st>>>(
+            reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+            static_cast<const double*>(d_ref_pack_cov.ptr), num_groups, B, multi_sk, partials);
+      else if (use_multi_mma)
         rmsd_multi_cov_mma_kernel<<<cov_grid, MULTI_THREADS, 0, st>>>(
             reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
             static_cast<const double*>(d_ref.ptr), num_groups, B, multi_sk, partials);
@@ -1264,6 +1279,7 @@ int rmsd_create(const cvp_rmsd_desc* desc, cvp_cv** out) {
       // workspace for (ceil(n / 1024) per group)
       cv->multi_sk_max = (int)std::max<int64_t>(1, std::min<int64_t>({16, n / 512, div_up(n, 1024)}));
       pk_pack_reference(cv->ref.data(), G, (int)n, cv->ref_pack);
+      cpk_pack_reference(cv->ref.data(), G, (int)n, cv->ref_pack_cov);
     }
   }
   *out = cv;

@@ -901,6 +901,146 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
   }
 }
 
+// ---- covariance, TMA-fed ----------------------------------------------------------------------------
+// Same idea for the forward contraction.  The references are packed once, per tile of MULTI_TG groups
+// and chunk of MMA_KA atoms, in B-fragment order (ref_pack_cov [group tile][chunk][k-step][12][32]);
+// the frames cannot be packed (they are the input), but their rows can be copied as they are: 32 bulk
+// copies of 16 atoms x 12 bytes per stage, one per lane of warp 0.  The A fragments are then read
+// from the raw float rows and widened in registers (3 LDS.32 + 3 F2F per 18 DMMA).  MMA row tile
+// 3 fb + c holds component c of frames 8 fb .. 8 fb + 7, which makes those loads conflict-free with
+// a row pitch of 52 floats: bank = 20 (lane / 4) + 3 (lane % 4) + const (mod 32), all distinct.
+// Needs first_atom, N and n multiples of 4 and aligned positions; otherwise the register-staged
+// kernel above runs.  Same partial-sum records, same summation order per record.
+constexpr int CPK_STAGES = 4;
+constexpr int CPK_XP = 52;                                  // floats per frame row of a stage
+constexpr int CPK_A_STAGE = MULTI_TF * CPK_XP;              // floats
+constexpr int CPK_B_STAGE = (MMA_KA / 4) * (MMA_ROWS / 8) * 32;  // doubles
+constexpr size_t MULTI_COV_PK_SMEM = CPK_STAGES * (sizeof(double) * CPK_B_STAGE + sizeof(float) * CPK_A_STAGE) +
+                                     2 * CPK_STAGES * sizeof(uint64_t);
+
+inline int cpk_chunks(int n) { return (n + MMA_KA - 1) / MMA_KA; }
+// host: the centred references [G][n][3] -> ref_pack_cov
+inline void cpk_pack_reference(const double* ref, int num_groups, int n, std::vector<double>& out) {
+  const int tiles = (num_groups + MULTI_TG - 1) / MULTI_TG, chunks = cpk_chunks(n);
+  out.assign((size_t)tiles * chunks * CPK_B_STAGE, 0.0);
+  for (int g = 0; g < num_groups; ++g)
+    for (int a = 0; a < n; ++a) {
+      double* block = out.data() + ((size_t)(g / MULTI_TG) * chunks + a / MMA_KA) * CPK_B_STAGE;
+      const int al = a % MMA_KA;
+      for (int d = 0; d < 3; ++d) {
+        const int q = 3 * (g % MULTI_TG) + d;
+        block[(((al >> 2) * (MMA_ROWS / 8) + (q >> 3)) << 5) + ((q & 7) << 2) + (al & 3)] =
+            ref[((size_t)g * n + a) * 3 + d];
+      }
+    }
+}
+
+// grid = (frame tiles, group tiles, SK), MULTI_THREADS threads, dynamic shared memory MULTI_COV_PK_SMEM
+__global__ void __launch_bounds__(MULTI_THREADS, 2)
+    rmsd_multi_cov_pk_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom, int n,
+                             const double* __restrict__ ref_pack_cov, int num_groups, int64_t num_frames,
+                             int SK, double* __restrict__ partials) {
+  extern __shared__ __align__(16) double multi_smem[];
+  double* bring = multi_smem;                                              // [CPK_STAGES][CPK_B_STAGE]
+  float* aring = reinterpret_cast<float*>(bring + CPK_STAGES * CPK_B_STAGE);  // [CPK_STAGES][32][CPK_XP]
+  uint64_t* full = reinterpret_cast<uint64_t*>(aring + CPK_STAGES * CPK_A_STAGE);
+  uint64_t* empty = full + CPK_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;  // frames 8 wm .. 8 wm + 7 (3 row tiles), column tiles 6 wn .. 6 wn + 5
+  const int64_t f0 = (int64_t)blockIdx.x * MULTI_TF;
+  const int g0 = blockIdx.y * MULTI_TG;
+  const int sk = blockIdx.z;
+  const int ns = num_groups * SK;
+  const int frames_here = (int)min((int64_t)MULTI_TF, num_frames - f0);
+  const int chunks_total = (n + MMA_KA - 1) / MMA_KA;
+  const int chunks_per = (chunks_total + SK - 1) / SK;
+  const int c_begin = min(chunks_total, sk * chunks_per);
+  const int c_end = min(chunks_total, (sk + 1) * chunks_per);
+  const int stages = c_end - c_begin;
+  const float* x_row = pos + ((f0 + min(lane, frames_here - 1)) * num_atoms + first_atom) * 3;
+  const double* b_src = ref_pack_cov + (size_t)blockIdx.y * chunks_total * CPK_B_STAGE;
+
+  // warp 0: stage s -> slot s % CPK_STAGES (lane = frame row; lane 0 also moves the reference block)
+  auto issue = [&](int s) {
+    const int slot = s % CPK_STAGES;
+    const int a = (c_begin + s) * MMA_KA;
+    const uint32_t row_bytes = (uint32_t)(min(MMA_KA, n - a) * 12);
+    if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)(CPK_B_STAGE * sizeof(double)) + row_bytes * frames_here);
+    __syncwarp();
+    if (lane == 0)
+      tma_load_1d(bring + (size_t)slot * CPK_B_STAGE, b_src + (size_t)(c_begin + s) * CPK_B_STAGE,
+                  CPK_B_STAGE * sizeof(double), &full[slot]);
+    if (lane < frames_here)
+      tma_load_1d(aring + (size_t)slot * CPK_A_STAGE + lane * CPK_XP, x_row + (int64_t)a * 3, row_bytes, &full[slot]);
+  };
+  // rows of frames past the batch and columns past the group are never copied: they must hold
+  // finite numbers (they meet zeros of the packed reference or rows that are not stored)
+  for (int e = tid; e < CPK_STAGES * CPK_A_STAGE; e += MULTI_THREADS) aring[e] = 0.f;
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < CPK_STAGES; ++k) {
+      mbar_init(&full[k], 1);
+      mbar_init(&empty[k], MULTI_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 0)
+    for (int s = 0; s < min(stages, CPK_STAGES); ++s) issue(s);
+
+  double acc[3][6][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int a_off = (8 * wm + (lane >> 2)) * CPK_XP + 3 * (lane & 3);
+  for (int s = 0; s < stages; ++s) {
+    const int slot = s % CPK_STAGES;
+    const uint32_t parity = (uint32_t)(s / CPK_STAGES) & 1u;
+    mbar_wait(&full[slot], parity);
+    const float* as = aring + (size_t)slot * CPK_A_STAGE + a_off;
+    const double* bs = bring + (size_t)slot * CPK_B_STAGE;
+#pragma unroll
+    for (int ks = 0; ks < MMA_KA / 4; ++ks) {
+      double a[3], b[6];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) a[i] = (double)as[12 * ks + i];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) b[j] = bs[((ks * (MMA_ROWS / 8) + 6 * wn + j) << 5) + lane];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dmma(acc[i][j], a[i], b[j]);
+    }
+    if (s + CPK_STAGES < stages) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+      if (warp == 0) {
+        mbar_wait(&empty[slot], parity);
+        issue(s + CPK_STAGES);
+      }
+    }
+  }
+  // C[row = lane / 4][col = 2 (lane % 4) + h] of tile (component i of frames 8 wm .., column tile 6 wn + j)
+  const int64_t f = f0 + 8 * wm + (lane >> 2);
+  if (f >= num_frames) return;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int q = 8 * (6 * wn + j) + 2 * (lane & 3) + h;
+        const int g = g0 + q / 3, d = q % 3;
+        if (g >= num_groups) continue;
+        partials[((size_t)f * ns + (size_t)g * SK + sk) * 13 + 4 + 3 * i + d] = acc[i][j][h];
+      }
+    }
+  }
+}
+
 constexpr size_t MULTI_GRAD_SMEM =
     2 * sizeof(double) * (MULTI_KG * MULTI_TF * 10 + MULTI_KG * MULTI_TA * 3);
 
