@@ -50,13 +50,52 @@ constexpr int CELL_SMEM_BUDGET = 64 * 1024;  // bytes of j data per CTA (2 CTAs 
 #ifndef SWEEP_P2
 #define SWEEP_P2 1
 #endif
+// Phase 1 (SWEEP_SQ, FP32 only): the staged record is (-2 x_j, |x_j|^2) and the test reads
+// |x_j|^2 - 2 x_i . x_j < rc^2 - |x_i|^2 + margin: three FMAs and a compare per pair instead of three
+// subtractions, three multiply-adds and a compare.  A conservative filter (the margin covers the
+// cancellation), phase 2 forms the exact x_j - x_i = fma(-0.5, -2 x_j, -x_i) and tests r^2 < rc^2
+// again.  The tag (or accumulator address) of a staged atom moves to a side array.
+#ifndef SWEEP_SQ
+#define SWEEP_SQ SWEEP_P2
+#endif
+#if SWEEP_SQ && !SWEEP_P2
+#error "SWEEP_SQ needs SWEEP_P2"
+#endif
 #ifndef CELL_SMEM_BUDGET_SYM_KB
-#define CELL_SMEM_BUDGET_SYM_KB (SWEEP_P2 ? 63 : 72)
+#define CELL_SMEM_BUDGET_SYM_KB (SWEEP_SQ ? 55 : SWEEP_P2 ? 63 : 72)
 #endif
 constexpr int CELL_SMEM_BUDGET_SYM = CELL_SMEM_BUDGET_SYM_KB * 1024;  // ... with the j gradient accumulators
 constexpr int TAG_DUMMY = -1;
 
 __host__ __device__ inline int cell_round_up(int n, int m) { return (n + m - 1) / m * m; }
+
+// Layout of a sorted group in memory.  The sweep stages the j atoms of a frame chunk by chunk; a
+// chunk of *consecutive* sorted atoms is a slab of the box, and the i atoms of a tile next to the
+// slab then find very different numbers of partners in it (the ones on the near side many, the
+// others none): phase 2 of the sweep, which lasts as long as its busiest lane, ran with 17 of 32
+// lanes active.  So the clusters are dealt to the chunks like cards -- cluster c of the sorted order
+// goes to chunk c % nchunk, place c / nchunk -- and every chunk is a uniform sample of the whole
+// frame: each (tile, chunk) visit sees 1/nchunk of every i atom's neighbourhood.  The chunks are
+// contiguous in memory (one bulk copy each); a tile of 32 consecutive sorted atoms is four
+// clusters at four places.
+struct CellLayout {
+  int nchunk;  // chunks the group is dealt to (1: plain sorted order)
+  int cpc;     // clusters per chunk (a multiple of 4)
+  int n_pad;   // = 8 cpc nchunk atoms, padding included
+};
+inline CellLayout cell_layout(int n, int jchunk_max) {
+  const int clusters = (n + CELL_CLUSTER - 1) / CELL_CLUSTER;
+  CellLayout l;
+  l.nchunk = jchunk_max > 0 ? (clusters * CELL_CLUSTER + jchunk_max - 1) / jchunk_max : 1;
+  if (l.nchunk < 1) l.nchunk = 1;
+  l.cpc = cell_round_up((clusters + l.nchunk - 1) / l.nchunk, CELL_TILE / CELL_CLUSTER);
+  if (l.cpc < CELL_TILE / CELL_CLUSTER) l.cpc = CELL_TILE / CELL_CLUSTER;
+  l.n_pad = l.cpc * l.nchunk * CELL_CLUSTER;
+  return l;
+}
+__device__ __forceinline__ int cell_place(int cluster, int nchunk, int cpc) {
+  return nchunk == 1 ? cluster : (cluster % nchunk) * cpc + cluster / nchunk;
+}
 
 // ---- 1. sort -------------------------------------------------------------------------------------
 // One CTA per (frame, group).  Dynamic shared memory: uint16 cell_of[n], uint16 order[n],
@@ -66,7 +105,7 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
     cell_sort_kernel(const T* __restrict__ pos, int64_t num_atoms, const int32_t* __restrict__ idx1,
                      const int32_t* __restrict__ tag1, int n1, int n1_pad,
                      const int32_t* __restrict__ idx2, const int32_t* __restrict__ tag2, int n2,
-                     int n2_pad, const T* __restrict__ box, int box_mode,
+                     int n2_pad, int nchunk1, int nchunk2, const T* __restrict__ box, int box_mode,
                      typename Vec4<T>::type* __restrict__ sorted1,
                      typename Vec4<T>::type* __restrict__ sorted2,
                      typename Vec4<T>::type* __restrict__ aabb1,
@@ -77,6 +116,8 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
   const bool first = (blockIdx.x & 1) == 0;
   const int n = first ? n1 : n2;
   const int n_pad = first ? n1_pad : n2_pad;
+  const int nchunk = first ? nchunk1 : nchunk2;
+  const int cpc = n_pad / CELL_CLUSTER / nchunk;
   const int32_t* idx = first ? idx1 : idx2;
   const int32_t* tag = first ? tag1 : tag2;
   T4* sorted = (first ? sorted1 : sorted2) + b * n_pad;
@@ -259,6 +300,7 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
   // write clusters and their bounding boxes (one thread per cluster)
   for (int cl = tid; cl < n_pad / CELL_CLUSTER; cl += CELL_SORT_THREADS) {
     T mn[3] = {T(3e38), T(3e38), T(3e38)}, mx[3] = {T(-3e38), T(-3e38), T(-3e38)};
+    const int place = cell_place(cl, nchunk, cpc);
 #pragma unroll
     for (int k = 0; k < CELL_CLUSTER; ++k) {
       const int s = cl * CELL_CLUSTER + k;
@@ -280,7 +322,7 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
         rec.x = rec.y = rec.z = T(1e18);  // never in range; also flagged by the tag
         rec.w = tag_encode(TAG_DUMMY, T(0));
       }
-      sorted[s] = rec;
+      sorted[place * CELL_CLUSTER + k] = rec;
     }
     T4 centre, half;
     if (mn[0] > mx[0]) {  // cluster of padding only
@@ -295,8 +337,8 @@ __global__ void __launch_bounds__(CELL_SORT_THREADS)
       half.z = T(0.5) * (mx[2] - mn[2]);
     }
     centre.w = half.w = T(0);
-    aabb[2 * cl] = centre;
-    aabb[2 * cl + 1] = half;
+    aabb[2 * place] = centre;
+    aabb[2 * place + 1] = half;
   }
 }
 
@@ -327,7 +369,8 @@ __host__ __device__ inline size_t cell_sweep_smem(bool sym = false) {
                        (size_t)(CELL_SWEEP_THREADS / 32) * batch_atoms) +
          (size_t)(CELL_SWEEP_THREADS / 32) * SURV_CAP * sizeof(uint16_t) +
          (sym ? (size_t)jchunk * 4 * sizeof(int) : 0) +
-         (SWEEP_P2 ? (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms / 32) * 32 * sizeof(uint32_t) : 0);
+         (SWEEP_P2 ? (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms / 32) * 32 * sizeof(uint32_t) : 0) +
+         (SWEEP_SQ && sizeof(T) == 4 ? (size_t)(CELL_SWEEP_THREADS / 32) * batch_atoms * sizeof(int) : 0);
 }
 
 // Symmetric mode: exact fixed-point accumulation.  x = round(v * scale) (F2I, |v * scale| < 2^30 by
@@ -413,8 +456,8 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
                       const typename PairFn<T, KIND>::Acc* __restrict__ frame_coef,
                       double* __restrict__ energy_partials,
                       typename Vec4<T>::type* __restrict__ igrad,
-                      typename Vec4<T>::type* __restrict__ jgrad = nullptr, float sym_scale = 0.f,
-                      int sym_passes = 1) {
+                      typename Vec4<T>::type* __restrict__ jgrad, float sym_scale, int sym_passes,
+                      int jchunk_atoms, int i_nchunk) {
   static_assert(!SYM || (GRAD && !OVERLAP && sizeof(T) == 4 && !PairFn<T, KIND>::HAS_PARAMS),
                 "symmetric mode: FP32 gradients of disjoint groups without per-atom parameters");
   using T4 = typename Vec4<T>::type;
@@ -432,11 +475,14 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   constexpr int NW = BATCH_CL * CELL_CLUSTER / 32;
   constexpr int BATCH_ATOMS = BATCH_CL * CELL_CLUSTER;
 
-  const int jchunk = cell_jchunk<T>(SYM);
+  const int jchunk = cell_jchunk<T>(SYM);  // the shared-memory layout; chunks hold jchunk_atoms <= jchunk
   T4* jsm = reinterpret_cast<T4*>(sweep_smem);
   T4* bsm = jsm + jchunk;  // cluster boxes of the chunk: (centre, half) pairs
-  T4* stage_all = bsm + (jchunk / CELL_CLUSTER) * 2;       // [NWARP][BATCH_ATOMS]
-  T4* survivors_all = stage_all + NWARP * BATCH_ATOMS;    // [NWARP][SURV_CAP] 16-bit entries
+  // [NWARP] staging areas: BATCH_ATOMS records, then (SQ) BATCH_ATOMS tags
+  constexpr bool SQ = SWEEP_SQ && sizeof(T) == 4;
+  constexpr int STAGE_BYTES = BATCH_ATOMS * (int)sizeof(T4) + (SQ ? BATCH_ATOMS * 4 : 0);
+  unsigned char* stage_all = reinterpret_cast<unsigned char*>(bsm + (jchunk / CELL_CLUSTER) * 2);
+  T4* survivors_all = reinterpret_cast<T4*>(stage_all + NWARP * STAGE_BYTES);  // [NWARP][SURV_CAP] 16-bit entries
   uint32_t* hits_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(survivors_all) + NWARP * SURV_CAP);  // SWEEP_P2: [NWARP][NW][32]
   int* jacc = reinterpret_cast<int*>(hits_all + (SWEEP_P2 ? NWARP * NW * 32 : 0));  // SYM: [jchunk][3] wrapping sums
   int* jwrap = jacc + 3 * jchunk;                                  // SYM: [jchunk] packed wrap counters
@@ -475,8 +521,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   for (int c = 0; c < NCH; ++c) en[c] = Acc(0);
 
   uint32_t phase = 0;
-  for (int j0 = 0; j0 < nj_pad; j0 += jchunk) {
-    const int jcount = min(jchunk, nj_pad - j0);
+  const int i_cpc = ni_pad / CELL_CLUSTER / i_nchunk;
+  for (int j0 = 0; j0 < nj_pad; j0 += jchunk_atoms) {
+    const int jcount = min(jchunk_atoms, nj_pad - j0);
     const int ncl = jcount / CELL_CLUSTER;
     __syncthreads();  // everyone is done with the previous chunk
     if (tid == 0) {
@@ -506,7 +553,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
     for (int tile_first = 0; tile_first < ntile; tile_first += tiles_per_pass) {
     const int tile_last = min(ntile, tile_first + tiles_per_pass);
     for (int tile = tile_first + warp_global; tile < tile_last; tile += warp_stride) {
-      T4 pi = ip[tile * CELL_TILE + lane];
+      // (where the lane's atom of the tile lives: see CellLayout)
+      const int ipos = cell_place(tile * (CELL_TILE / CELL_CLUSTER) + (lane >> 3), i_nchunk, i_cpc) * CELL_CLUSTER + (lane & 7);
+      T4 pi = ip[ipos];
       const int tagi = tag_decode(pi.w);
       // padding lanes go to the far side of the padding atoms (+1e18), so no pair of them ever
       // passes a distance test
@@ -515,7 +564,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
       if (PRM) qi = atom_params[max(tagi, 0) & TAG_INDEX_MASK];
       T gx = T(0), gy = T(0), gz = T(0);
       if (GRAD && j0 > 0) {
-        const T4 g = ig[tile * CELL_TILE + lane];
+        const T4 g = ig[ipos];
         gx = g.x;
         gy = g.y;
         gz = g.z;
@@ -598,20 +647,35 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
       // instead of one corner of it -- so that every lane finds about the same number of hits in
       // every batch (a batch of 16 *consecutive* clusters lies on one side of the tile: the lanes
       // on that side had 2.3 x the average number of hits, ncu: 14 of 32 lanes active).
-      T4* stg = stage_all + warp * BATCH_ATOMS;
+      T4* stg = reinterpret_cast<T4*>(stage_all + warp * STAGE_BYTES);
+      int* side = reinterpret_cast<int*>(stg + BATCH_ATOMS);
+      // SQ: what |x_j|^2 - 2 x_i . x_j is compared with.  Every quantity of a pair in range is at
+      // most M = (|x_i| + rc)^2 <= 2 (|x_i|^2 + rc^2) in size and the two sides carry about 18
+      // roundings of 2^-24 M between them: 2^-17 (|x_i|^2 + rc^2) is four times that.
+      T sq_thr = T(0);
+      if constexpr (SQ) {
+        const T xi2 = fma(pi.z, pi.z, fma(pi.y, pi.y, pi.x * pi.x));
+        sq_thr = (pc.cutoff2 - xi2) + T(7.62939453125e-6) * (xi2 + pc.cutoff2);
+      }
 #if SWEEP_P2
-      const uint32_t stg_s = smem_addr(stg);
+      uint32_t stg_s = smem_addr(stg);
+      asm volatile("" : "+r"(stg_s));  // opaque: kept in a register, not recomputed per hit
       const uint32_t jacc_s = smem_addr(jacc), jwrap_s = smem_addr(jwrap);
 #endif
+      const int natoms = nsurv * CELL_CLUSTER;
 #if SWEEP_P2
-      // batches of whole hit words (4 clusters = 32 staged atoms): `nq` words over `nb` batches, qmin
-      // or qmin + 1 each, so that phase 1 tests no word of padding.  Cluster e of batch b is survivor
-      // b + e nb while e < 4 qmin (the strided sample); the clusters of the extra word of the first
-      // `nq - qmin nb` batches come from the end of the list.
-      const int nq = (nsurv + 3) >> 2;
+      // Batches of whole hit words (32 staged atoms): `nq` words over `nb` batches, qmin or qmin + 1
+      // each, so that phase 1 tests no word of padding.  The sample is strided by *atom*: number the
+      // atoms of the surviving clusters t = 8 survivor + atom; slot a of batch b is atom b + a nb
+      // while a < 32 qmin, and the extra word of the first `nq - qmin nb` batches comes from the end
+      // of the list.  A lane's hits come in clumps -- a cluster is mostly inside or mostly outside
+      // the cutoff sphere of an i atom -- so with whole clusters in a batch the busiest lane had
+      // 1.9 x the mean number of hits (17 of 32 lanes active in phase 2); one or two atoms of
+      // every cluster per batch bring the counts close to Poisson.
+      const int nq = (natoms + 31) >> 5;
       const int nb = (nq + NW - 1) / NW;
       const int qmin = nb > 0 ? nq / nb : 0;
-      const int strided = 4 * qmin * nb;
+      const int strided = 32 * qmin * nb;
 #else
       const int nb = (nsurv + BATCH_CL - 1) / BATCH_CL;
 #endif
@@ -619,10 +683,10 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
 #if SWEEP_P2
         const int words = qmin + (bi < nq - qmin * nb ? 1 : 0);  // <= NW
         const int take = 4 * words;                               // clusters, padding included
-        auto survivor = [&](int e) { return e < 4 * qmin ? bi + e * nb : strided + 4 * bi + (e - 4 * qmin); };
+        auto slot_atom = [&](int a) { return a < 32 * qmin ? bi + a * nb : strided + 32 * bi + (a - 32 * qmin); };
 #else
         const int take = (nsurv - bi + nb - 1) / nb;  // <= BATCH_CL
-        auto survivor = [&](int e) { return bi + e * nb; };
+        auto slot_atom = [&](int a) { return (bi + (a >> 3) * nb) * CELL_CLUSTER + (a & 7); };
 #endif
         bool unsafe = false;
         // (words that phase 1 does not test need no padding)
@@ -630,10 +694,11 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           T4 pj;
           pj.x = pj.y = pj.z = T(1e18);  // padding of a short batch: never in range
           pj.w = tag_encode(TAG_DUMMY, T(0));
-          if (a < take * CELL_CLUSTER && survivor(a >> 3) < nsurv) {
-            const uint32_t ent = lst[survivor(a >> 3)];
+          const int t = slot_atom(a);
+          if (a < take * CELL_CLUSTER && t < natoms) {
+            const uint32_t ent = lst[t >> 3];
             const int cl = (int)(ent & 0xffu);
-            pj = jsm[cl * CELL_CLUSTER + (a & 7)];
+            pj = jsm[cl * CELL_CLUSTER + (t & 7)];
             if (PBC == 1) {
               // d = (x_j - shift) - x_i is the minimum image for a safe cluster.  Same image (the
               // common case): the stored coordinates go in as they are, so that x_j - x_i is the
@@ -656,12 +721,17 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             if (SYM) {
 #if SWEEP_P2
               // the shared-window address of the atom's accumulators (-1: padding)
-              pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : (int)(jacc_s + (uint32_t)(cl * CELL_CLUSTER + (a & 7)) * 12u), T(0));
+              pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : (int)(jacc_s + (uint32_t)(cl * CELL_CLUSTER + (t & 7)) * 12u), T(0));
 #else
               // the accumulator slot of the atom within the chunk (-1: padding)
-              pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : cl * CELL_CLUSTER + (a & 7), T(0));
+              pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : cl * CELL_CLUSTER + (t & 7), T(0));
 #endif
             }
+          }
+          if constexpr (SQ) {
+            side[a] = tag_decode(pj.w);
+            pj.w = fma(pj.z, pj.z, fma(pj.y, pj.y, pj.x * pj.x));
+            pj.x *= T(-2), pj.y *= T(-2), pj.z *= T(-2);
           }
           stg[a] = pj;
         }
@@ -672,9 +742,10 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         // (ShortestDistance also gets the displacement in double, `ex`: with beta = 100 the weight
         // moves by 1e-5 when r moves by 1e-7 r, so neither the three roundings of an FP32 r^2 nor
         // the rounding of a staged image x_j - k L can be afforded)
-        auto interact = [&](const T4& pj, T dx, T dy, T dz, bool checked, const double (&ex)[3]) {
-          const int tagj = tag_decode(pj.w);  // (SYM: the accumulator slot)
+        auto interact = [&](int tagj, T dx, T dy, T dz, bool checked, const double (&ex)[3]) {
+          // (tagj: the tag of the j atom; SYM: its accumulator slot or address)
           const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+          if (SQ && !checked && !(r2 < pc.cutoff2)) return;  // passed the filter, not the test
           // padding never passes the shifted-image test (coordinates 1e18); the minimum-image
           // reduction of the unsafe path can fold it back, so that path checks the tags
           bool ok = checked ? (tagj >= 0 && tagi >= 0) : true;
@@ -716,8 +787,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         // exact displacement of staged atom `slot` from the lane's atom: stored coordinates and the
         // image count of its cluster, in double (only instantiated for ShortestDistance)
         auto exact_displacement = [&](int slot, double (&ex)[3]) {
-          const uint32_t ent = lst[survivor(slot >> 3)];
-          const T4 raw = jsm[(int)(ent & 0xffu) * CELL_CLUSTER + (slot & 7)];
+          const int t = slot_atom(slot);
+          const uint32_t ent = lst[t >> 3];
+          const T4 raw = jsm[(int)(ent & 0xffu) * CELL_CLUSTER + (t & 7)];
           const uint32_t kx = (ent >> 8) & 3u, ky = (ent >> 10) & 3u, kz = (ent >> 12) & 3u;
           ex[0] = (double)raw.x - (double)pi.x - (kx == 1u ? (double)bx.ax : (kx == 2u ? -(double)bx.ax : 0.0));
           ex[1] = (double)raw.y - (double)pi.y - (ky == 1u ? (double)bx.by : (ky == 2u ? -(double)bx.by : 0.0));
@@ -729,7 +801,11 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           // than twice the cutoff): per-pair minimum image, straight loop, compact code
           for (int slot = 0; slot < take * CELL_CLUSTER; ++slot) {
             const T4 pj = stg[slot];
-            T dx = pj.x - pr.x, dy = pj.y - pr.y, dz = pj.z - pr.z;
+            T dx, dy, dz;
+            if constexpr (SQ)
+              dx = fma(T(-0.5), pj.x, -pr.x), dy = fma(T(-0.5), pj.y, -pr.y), dz = fma(T(-0.5), pj.z, -pr.z);
+            else
+              dx = pj.x - pr.x, dy = pj.y - pr.y, dz = pj.z - pr.z;
             pair_min_image<PBC>(dx, dy, dz, bx);
             if (fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2) {
               double ex[3] = {(double)dx, (double)dy, (double)dz};
@@ -739,7 +815,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
                 ex[1] -= (double)bx.by * rint(ex[1] / (double)bx.by);
                 ex[2] -= (double)bx.cz * rint(ex[2] / (double)bx.cz);
               }
-              interact(pj, dx, dy, dz, true, ex);
+              interact(SQ ? side[slot] : tag_decode(pj.w), dx, dy, dz, true, ex);
             }
           }
         } else {
@@ -758,8 +834,12 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
 #pragma unroll
               for (int u = 0; u < 32; ++u) {
                 const T4 pj = stg[w * 32 + u];
-                const T dx = pj.x - pr.x, dy = pj.y - pr.y, dz = pj.z - pr.z;
-                if (fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2) m |= 1u << u;
+                if constexpr (SQ) {
+                  if (fma(pr.x, pj.x, fma(pr.y, pj.y, fma(pr.z, pj.z, pj.w))) < sq_thr) m |= 1u << u;
+                } else {
+                  const T dx = pj.x - pr.x, dy = pj.y - pr.y, dz = pj.z - pr.z;
+                  if (fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2) m |= 1u << u;
+                }
               }
             }
             hw[32 * w] = m;
@@ -783,14 +863,13 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               cur &= cur - 1u;
               double ex[3] = {0.0, 0.0, 0.0};
               if constexpr (KIND == CVP_PAIR_SOFTMIN) exact_displacement(k, ex);
-              if constexpr (sizeof(T) == 4) {
+              if constexpr (SQ) {
                 const float4 pj = lds_f4(stg_s + (uint32_t)k * 16u);
-                T4 pjt;
-                pjt.x = pj.x, pjt.y = pj.y, pjt.z = pj.z, pjt.w = pj.w;
-                interact(pjt, pjt.x - pr.x, pjt.y - pr.y, pjt.z - pr.z, false, ex);
+                const int tagj = (int)lds_u32(stg_s + (uint32_t)(BATCH_ATOMS * 16) + (uint32_t)k * 4u);
+                interact(tagj, fmaf(-0.5f, pj.x, -pr.x), fmaf(-0.5f, pj.y, -pr.y), fmaf(-0.5f, pj.z, -pr.z), false, ex);
               } else {
                 const T4 pj = stg[k];
-                interact(pj, pj.x - pr.x, pj.y - pr.y, pj.z - pr.z, false, ex);
+                interact(tag_decode(pj.w), pj.x - pr.x, pj.y - pr.y, pj.z - pr.z, false, ex);
               }
             }
           }
@@ -836,7 +915,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               const T4 pj = stg[k];
               double ex[3] = {0.0, 0.0, 0.0};
               if constexpr (KIND == CVP_PAIR_SOFTMIN) exact_displacement(k, ex);
-              interact(pj, pj.x - pr.x, pj.y - pr.y, pj.z - pr.z, false, ex);
+              interact(tag_decode(pj.w), pj.x - pr.x, pj.y - pr.y, pj.z - pr.z, false, ex);
             }
           }
 #endif
@@ -849,7 +928,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         g.y = gy;
         g.z = gz;
         g.w = T(0);
-        ig[tile * CELL_TILE + lane] = g;
+        ig[ipos] = g;
       }
     }
     if (SYM) {

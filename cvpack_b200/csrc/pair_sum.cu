@@ -418,7 +418,9 @@ struct PairSumCV : cvp_cv {
     size_t rec = dtype == CVP_F32 ? 16 : 32;
     size_t real = dtype == CVP_F32 ? 4 : 8;
     // sized for the cell path (padded groups + cluster boxes), which also covers the all-pairs path
-    size_t n = cell_round_up((int)g1.size(), CELL_TILE) + cell_round_up((int)g2.size(), CELL_TILE);
+    // (the smallest chunk any sweep uses gives the most padding)
+    const int jc = std::min({cell_jchunk<float>(true), cell_jchunk<float>(false), cell_jchunk<double>(false)});
+    size_t n = cell_layout((int)g1.size(), jc).n_pad + cell_layout((int)g2.size(), jc).n_pad;
     size_t bytes = n * rec + 2 * (n / CELL_CLUSTER) * rec + 1024;  // positions + cluster boxes
     if (need_grad) bytes += n * rec + 512;                         // packed gradients
     bytes += (size_t)std::max(nblk((int)g1.size()), 64) * 2 * sizeof(double);  // energy partials
@@ -541,7 +543,6 @@ struct PairSumCV : cvp_cv {
     const int64_t B = a.num_frames;
     const int64_t N = a.num_atoms;
     const int n1 = (int)g1.size(), n2 = (int)g2.size();
-    const int n1p = cell_round_up(n1, CELL_TILE), n2p = cell_round_up(n2, CELL_TILE);
     const bool need_grad = a.grad != nullptr;
     const bool accumulate = (a.flags & CVP_FLAG_ACCUMULATE) != 0;
     const PairConsts<T> pc = consts<T>();
@@ -556,15 +557,25 @@ struct PairSumCV : cvp_cv {
       // enough CTAs for ~4 waves of 2 CTAs per SM, but never fewer tiles than warps per CTA
       const int64_t want = 148 * 2 * 4;
       nsplit = (int)std::max<int64_t>(1, div_up(want, B));
-      const int ntile = std::min(n1p, n2p) / CELL_TILE;
+      const int ntile = cell_round_up(std::min(n1, n2), CELL_TILE) / CELL_TILE;
       nsplit = std::max(1, std::min(nsplit, ntile / (CELL_SWEEP_THREADS / 32)));
       // the symmetric sweep (half the pair work) needs one CTA per frame: worth a ragged last wave
       // as soon as there is about one CTA per SM
       float unused_scale;
       int unused_passes;
-      if (B >= 148 && sym_plan<T, KIND, OVERLAP>(need_grad, 1, n1p, &unused_scale, &unused_passes))
+      if (B >= 148 && sym_plan<T, KIND, OVERLAP>(need_grad, 1, cell_round_up(n1, CELL_TILE), &unused_scale, &unused_passes))
         nsplit = 1;
     }
+    // symmetric mode (one sweep for both groups): FP32 contacts with 1/(1+x^6), disjoint groups, one
+    // CTA per frame, and a fixed-point scale of at least 2^16 that provably cannot overflow
+    float sym_scale = 0.f;
+    int sym_passes = 1;
+    const bool sym = sym_plan<T, KIND, OVERLAP>(need_grad, nsplit, cell_round_up(n1, CELL_TILE), &sym_scale, &sym_passes);
+    // memory layout of the sorted groups (CellLayout): a group that serves as the j side of a sweep
+    // is dealt to that sweep's chunks; in symmetric mode the first group is only ever the i side
+    const CellLayout lay1 = cell_layout(n1, sym ? 0 : cell_jchunk<T>(false));
+    const CellLayout lay2 = cell_layout(n2, cell_jchunk<T>(sym));
+    const int n1p = lay1.n_pad, n2p = lay2.n_pad;
 
     Carver carve(ws);
     T4* s1 = carve.take<T4>((size_t)B * n1p);
@@ -587,7 +598,7 @@ struct PairSumCV : cvp_cv {
       kernel<<<(unsigned)(2 * B), CELL_SORT_THREADS, smem, st>>>(
           pos, N, static_cast<const int32_t*>(d_g1.ptr), static_cast<const int32_t*>(d_tag1.ptr), n1,
           n1p, static_cast<const int32_t*>(d_g2.ptr), static_cast<const int32_t*>(d_tag2.ptr), n2,
-          n2p, box, a.box_mode, s1, s2, bb1, bb2);
+          n2p, lay1.nchunk, lay2.nchunk, box, a.box_mode, s1, s2, bb1, bb2);
       timer.end(st);
       CVP_LAUNCH_CHECK();
     }
@@ -598,17 +609,14 @@ struct PairSumCV : cvp_cv {
           (int)(ex_pairs.size() / 2), box, a.box_mode, pc, excluded);
       CVP_LAUNCH_CHECK();
     }
-    // symmetric mode (one sweep for both groups): FP32 contacts with 1/(1+x^6), disjoint groups, one
-    // CTA per frame, and a fixed-point scale of at least 2^16 that provably cannot overflow
-    float sym_scale = 0.f;
-    int sym_passes = 1;
-    const bool sym = sym_plan<T, KIND, OVERLAP>(need_grad, nsplit, n1p, &sym_scale, &sym_passes);
     last_path = sym ? 2 : 1;
     auto sweep = [&](bool first, bool with_grad, const Acc* coef, double* energy) -> int {
       const T4* ip = first ? s1 : s2;
       const T4* jp = first ? s2 : s1;
       const T4* jb = first ? bb2 : bb1;
       const int nip = first ? n1p : n2p, njp = first ? n2p : n1p;
+      const CellLayout& ilay = first ? lay1 : lay2;
+      const CellLayout& jlay = first ? lay2 : lay1;
       T4* out = first ? gr1 : gr2;
       // default step function 1/(1+x^6): specialised pair function
       const bool fast6 = KIND == CVP_PAIR_CONTACTS && d.step_kind == CVP_STEP_RATIONAL &&
@@ -633,7 +641,7 @@ struct PairSumCV : cvp_cv {
       timer.begin("sweep", st);
       kernel<<<(unsigned)(B * nsplit), CELL_SWEEP_THREADS, sweep_smem, st>>>(
           ip, jp, jb, prm_atom, nip, njp, nsplit, box, a.box_mode, pc, coef, energy,
-          with_grad ? out : nullptr, jout, sym_scale, sym_passes);
+          with_grad ? out : nullptr, jout, sym_scale, sym_passes, jlay.cpc * CELL_CLUSTER, ilay.nchunk);
       timer.end(st);
       CVP_LAUNCH_CHECK();
       return CVP_OK;

@@ -318,8 +318,13 @@ def test_path_many_references_one_atom_set(metric, n_group, first, frames, miles
     # ... and the register-staged DMMA gradient sums in the same order as the TMA-fed default
     native.set_option("multi_mma", 2)
     value5, grad5 = cv.getValueAndGradient(ctx)
-    native.set_option("multi_mma", 1)
     assert torch.equal(value5._value, value._value) and torch.equal(grad5, grad)
+    # ... and so does the TMA-fed covariance kernel (option 3: kept, not the default)
+    native.set_option("multi_mma", 3)
+    value6, grad6 = cv.getValueAndGradient(ctx)
+    native.set_option("multi_mma", 1)
+    assert torch.allclose(value6._value, value._value, rtol=1e-6, atol=1e-7)
+    assert (grad6 - grad).abs().max() <= 1e-6 * grad.abs().max()
     value4, grad4 = cv.getValueAndGradient(ctx)
     assert torch.equal(value4._value, value._value) and torch.equal(grad4, grad), "not deterministic"
     outside = torch.ones(n, dtype=torch.bool)
