@@ -145,10 +145,11 @@ int cvp_evaluate(cvp_cv* cv, int dtype, const void* positions, const void* box, 
   const bool need_grad = grad != nullptr;
   const int64_t chunk = frames_per_chunk(cv, dtype, need_grad, num_frames);
   const size_t bytes = cv->workspace_fixed(dtype) + (size_t)chunk * cv->workspace_per_frame(dtype, need_grad);
-  if (bytes > cv->workspace.bytes) {
+  DeviceBuffer& workspace = cv->workspace_select ? cv->workspace_alt : cv->workspace;
+  if (bytes > workspace.bytes) {
     // growing frees the old allocation: make sure nothing queued earlier still uses it
-    if (cv->workspace.ptr) CVP_CUDA_CHECK(cudaDeviceSynchronize());
-    if ((status = cv->workspace.reserve(bytes)) != CVP_OK) return status;
+    if (workspace.ptr) CVP_CUDA_CHECK(cudaDeviceSynchronize());
+    if ((status = workspace.reserve(bytes)) != CVP_OK) return status;
   }
   const size_t es = elem_size(dtype);
   for (int64_t first = 0; first < num_frames; first += chunk) {
@@ -165,7 +166,7 @@ int cvp_evaluate(cvp_cv* cv, int dtype, const void* positions, const void* box, 
     a.grad = need_grad ? static_cast<char*>(grad) + (size_t)first * num_atoms * 3 * es : nullptr;
     a.flags = flags;
     a.stream = static_cast<cudaStream_t>(stream);
-    if ((status = cv->run(a, cv->workspace.ptr)) != CVP_OK) return status;
+    if ((status = cv->run(a, workspace.ptr)) != CVP_OK) return status;
   }
   return CVP_OK;
 }
@@ -194,7 +195,30 @@ int evaluate_host_impl(cvp_cv* cv, int dtype, const void* positions, const void*
   // chunk: at most ~256 MiB of coordinates, at least 1 frame, and >= 4 chunks when possible
   int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t(256) << 20) / frame_bytes));
   chunk = std::min(chunk, std::max<int64_t>(1, (num_frames + 3) / 4));
-  constexpr int SLOTS = HostPipeline::SLOTS;
+  // The first copy in and the last copy out overlap nothing: a short first and a short last chunk
+  // (a quarter of a chunk, but a whole number of 148-frame waves so that the kernels take the same
+  // path as for the long chunks) shorten both; the frames in between go in equal chunks.
+  std::vector<int64_t> sizes;
+  {
+    const int64_t edge = (chunk / 4 + 147) / 148 * 148;
+    if (chunk >= 592 && num_frames >= 2 * edge + chunk) {
+      const int64_t rest = num_frames - 2 * edge;
+      const int64_t middle = (rest + chunk - 1) / chunk;
+      sizes.push_back(edge);
+      for (int64_t m = 0; m < middle; ++m) sizes.push_back(rest / middle + (m < rest % middle ? 1 : 0));
+      sizes.push_back(edge);
+    } else {
+      for (int64_t first = 0; first < num_frames; first += chunk) sizes.push_back(std::min(chunk, num_frames - first));
+    }
+  }
+  // Pipeline slots (staging buffers + stream): two, so that the copies of one chunk overlap the
+  // kernels of the other.  A spec that can run twice at once (concurrent_runs(): two workspaces)
+  // gets four: the kernels of chunks i and i + 1 overlap -- the tail of a launch, when SMs run out
+  // of CTAs, fills with the next chunk -- and chunk i + 2, whose kernels wait for the workspace of
+  // chunk i, has its coordinates on the device long before.
+  const bool concurrent = cv->concurrent_runs();
+  const int SLOTS = concurrent ? 4 : 2;
+  static_assert(HostPipeline::SLOTS >= 4, "slots");
   HostPipeline& hp = cv->host;
   const bool trace = std::getenv("CVP_HOST_TIMING") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
@@ -237,7 +261,24 @@ int evaluate_host_impl(cvp_cv* cv, int dtype, const void* positions, const void*
                               cudaMemcpyHostToDevice));
   }
   // the spec's workspace is shared by both slots: kernels of consecutive chunks are serialised by
-  // an event chain, copies are not
+  // an event chain, copies are not -- unless the spec can run twice at once (concurrent_runs()):
+  // then every slot has its own workspace and only the stream order of a slot remains
+  {
+    // workspaces sized for the longest chunk before anything is queued (growing one later would
+    // have to wait for the device)
+    if ((status = prepare(cv)) != CVP_OK) return status;
+    const int64_t longest = *std::max_element(sizes.begin(), sizes.end());
+    const size_t bytes = cv->workspace_fixed(dtype) +
+                         (size_t)frames_per_chunk(cv, dtype, need_grad, longest) *
+                             cv->workspace_per_frame(dtype, need_grad);
+    for (DeviceBuffer* buffer : {&cv->workspace, &cv->workspace_alt}) {
+      if (buffer == &cv->workspace_alt && !concurrent) continue;
+      if (bytes > buffer->bytes) {
+        if (buffer->ptr) CVP_CUDA_CHECK(cudaDeviceSynchronize());
+        if ((status = buffer->reserve(bytes)) != CVP_OK) return status;
+      }
+    }
+  }
   const double setup_ms = ms_since(t_start);
   const auto t_loop = now();
   auto drain = [&]() {
@@ -254,10 +295,20 @@ int evaluate_host_impl(cvp_cv* cv, int dtype, const void* positions, const void*
   } while (0)
   int64_t index = 0;
   status = CVP_OK;
-  for (int64_t first = 0; first < num_frames && status == CVP_OK; first += chunk, ++index) {
+  // CVP_HOST_TIMING: device timestamps per chunk (copy in done, kernels done, copy out done)
+  std::vector<cudaEvent_t> marks;
+  auto mark = [&](cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    marks.push_back(e);
+  };
+  for (int64_t first = 0; first < num_frames && status == CVP_OK; first += sizes[index], ++index) {
     const int k = (int)(index % SLOTS);
     cudaStream_t stream = hp.stream[k];
-    const int64_t count = std::min(chunk, num_frames - first);
+    const int64_t count = sizes[index];
+    mark(stream);
     CVP_HOST_CHECK(cudaMemcpyAsync(hp.pos[k].ptr,
                                    static_cast<const char*>(positions) + (size_t)first * frame_bytes,
                                    (size_t)count * frame_bytes, cudaMemcpyHostToDevice, stream));
@@ -268,13 +319,19 @@ int evaluate_host_impl(cvp_cv* cv, int dtype, const void* positions, const void*
                                      (size_t)count * 9 * es, cudaMemcpyHostToDevice, stream));
       dbox = hp.box[k].ptr;
     }
-    if (index > 0)
-      CVP_HOST_CHECK(cudaStreamWaitEvent(stream, hp.kernels_done[(index - 1) % SLOTS], 0));
+    mark(stream);
+    // the previous user of the workspace: chunk i - 1, or chunk i - 2 with two workspaces
+    const int64_t back = concurrent ? 2 : 1;
+    if (index >= back)
+      CVP_HOST_CHECK(cudaStreamWaitEvent(stream, hp.kernels_done[(index - back) % SLOTS], 0));
+    cv->workspace_select = concurrent ? (int)(index % 2) : 0;
     status = cvp_evaluate(cv, dtype, hp.pos[k].ptr, have_box ? dbox : nullptr,
                           have_box ? box_mode : CVP_BOX_NONE, count, num_atoms, hp.value[k].ptr,
                           need_grad ? hp.grad[k].ptr : nullptr, flags, stream);
+    cv->workspace_select = 0;
     if (status != CVP_OK) break;
     CVP_HOST_CHECK(cudaEventRecord(hp.kernels_done[k], stream));
+    mark(stream);
     CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(value) + (size_t)first * es, hp.value[k].ptr,
                                    (size_t)count * es, cudaMemcpyDeviceToHost, stream));
     if (emass != nullptr) {
@@ -289,8 +346,18 @@ int evaluate_host_impl(cvp_cv* cv, int dtype, const void* positions, const void*
       CVP_HOST_CHECK(cudaMemcpyAsync(static_cast<char*>(grad) + (size_t)first * frame_bytes,
                                      hp.grad[k].ptr, (size_t)count * frame_bytes,
                                      cudaMemcpyDeviceToHost, stream));
+    mark(stream);
   }
   drain();
+  if (trace && !marks.empty()) {
+    for (size_t m = 0; m + 3 < marks.size(); m += 4) {
+      float t[4];
+      for (int q = 0; q < 4; ++q) cudaEventElapsedTime(&t[q], marks[0], marks[m + q]);
+      fprintf(stderr, "[cvp_evaluate_host] chunk %zu (%lld frames): copy in %.1f-%.1f, kernels -%.1f, copy out -%.1f ms\n",
+              m / 4, (long long)sizes[m / 4], t[0], t[1], t[2], t[3]);
+    }
+    for (cudaEvent_t e : marks) cudaEventDestroy(e);
+  }
   cudaError_t last = cudaGetLastError();
   if (trace)
     fprintf(stderr,

@@ -167,10 +167,10 @@ namespace cvp {
 // Device staging buffers, streams and events of the host-buffer path (cvp_evaluate_host); they live
 // as long as the spec so that repeated calls neither allocate nor free device memory.
 struct HostPipeline {
-  static constexpr int SLOTS = 2;
+  static constexpr int SLOTS = 4;  // two in use unless the spec can run two chunks at once
   DeviceBuffer pos[SLOTS], grad[SLOTS], value[SLOTS], box[SLOTS], emass[SLOTS], shared_box, masses;
-  cudaStream_t stream[SLOTS] = {nullptr, nullptr};
-  cudaEvent_t kernels_done[SLOTS] = {nullptr, nullptr};
+  cudaStream_t stream[SLOTS] = {};
+  cudaEvent_t kernels_done[SLOTS] = {};
   int ensure() {
     for (int k = 0; k < SLOTS; ++k) {
       if (!stream[k]) CVP_CUDA_CHECK(cudaStreamCreateWithFlags(&stream[k], cudaStreamNonBlocking));
@@ -210,11 +210,18 @@ struct cvp_cv {
   int64_t workspace_limit = int64_t(4) << 30;  // per spec and evaluate call (cvp_set_workspace_limit)
   std::vector<int32_t> active_atoms;  // sorted, unique
   cvp::DeviceBuffer workspace;
+  // A second workspace for the host path: specs whose run() touches nothing but its workspace and
+  // constant tables (concurrent_runs()) get one per pipeline slot, so that the kernels of
+  // consecutive chunks may overlap (the tail of one launch fills with the CTAs of the next).
+  cvp::DeviceBuffer workspace_alt;
+  int workspace_select = 0;  // which of the two cvp_evaluate uses (set by the host path only)
+  virtual bool concurrent_runs() const { return false; }
   cvp::DeviceBuffer grad_scratch;  // cvp_evaluate_with_mass: gradients that never leave the library
   virtual ~cvp_cv() {
     timer.clear();
     host.release();
     workspace.release();
+    workspace_alt.release();
     grad_scratch.release();
   }
   // Upload index/parameter arrays to the current device.

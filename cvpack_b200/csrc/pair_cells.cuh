@@ -55,6 +55,9 @@ constexpr int CELL_SMEM_BUDGET = 64 * 1024;  // bytes of j data per CTA (2 CTAs 
 // subtractions, three multiply-adds and a compare.  A conservative filter (the margin covers the
 // cancellation), phase 2 forms the exact x_j - x_i = fma(-0.5, -2 x_j, -x_i) and tests r^2 < rc^2
 // again.  The tag (or accumulator address) of a staged atom moves to a side array.
+#ifndef SWEEP_ATOM_STRIDE
+#define SWEEP_ATOM_STRIDE 1
+#endif
 #ifndef SWEEP_SQ
 #define SWEEP_SQ SWEEP_P2
 #endif
@@ -683,7 +686,14 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
 #if SWEEP_P2
         const int words = qmin + (bi < nq - qmin * nb ? 1 : 0);  // <= NW
         const int take = 4 * words;                               // clusters, padding included
+#if SWEEP_ATOM_STRIDE
         auto slot_atom = [&](int a) { return a < 32 * qmin ? bi + a * nb : strided + 32 * bi + (a - 32 * qmin); };
+#else
+        auto slot_atom = [&](int a) {  // strided by cluster
+          const int e = a >> 3;
+          return (e < 4 * qmin ? bi + e * nb : (strided >> 3) + 4 * bi + (e - 4 * qmin)) * CELL_CLUSTER + (a & 7);
+        };
+#endif
 #else
         const int take = (nsurv - bi + nb - 1) / nb;  // <= BATCH_CL
         auto slot_atom = [&](int a) { return (bi + (a >> 3) * nb) * CELL_CLUSTER + (a & 7); };

@@ -461,6 +461,8 @@ struct PairSumCV : cvp_cv {
            cell_sort_smem((int)std::max(g1.size(), g2.size())) <= limit;
   }
   size_t workspace_fixed(int) const override { return 8 * 256; }
+  // run() writes to its workspace only (the tables of the spec are read-only after upload)
+  bool concurrent_runs() const override { return true; }
   int64_t max_frames_per_run() const override {
     int64_t blocks = std::max(nblk((int)g1.size()), nblk((int)g2.size()));
     return std::max<int64_t>(1, (int64_t(1) << 31) / blocks - 1);
