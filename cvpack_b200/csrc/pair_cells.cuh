@@ -603,8 +603,12 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
       // Survivors go to this warp's list as (cluster, shift code, needs-minimum-image flag); the list
       // is complete before anything is staged, because the batches below take their clusters from
       // all over it.
-      uint16_t* lst = reinterpret_cast<uint16_t*>(survivors_all) + warp * SURV_CAP;
-      int nsurv = 0;
+      // Clusters that one shift serves (*safe*, nearly all) fill the list from the front; the ones too
+      // wide for that (box barely larger than twice the cutoff, or a sparse group whose tiles and
+      // clusters are large) fill it from the back and get batches of their own below: a batch with a
+      // single unsafe atom would take the per-pair minimum-image path as a whole.
+      uint16_t* lst_all = reinterpret_cast<uint16_t*>(survivors_all) + warp * SURV_CAP;
+      int nsafe = 0, nunsafe = 0;
       for (int c0 = 0; c0 < ncl; c0 += 32) {
         const int c = c0 + lane;
         bool near = false, safe = true;
@@ -632,11 +636,14 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           // clusters made of padding only sit at 1e18: the periodic shift would fold them back
           near = d2 < pc.cutoff2 && cj.x < T(1e17);
         }
-        const uint32_t cmask = __ballot_sync(FULL, near);
-        if (near)
-          lst[nsurv + __popc(cmask & ((1u << lane) - 1u))] =
-              (uint16_t)((uint32_t)c | code | (safe ? 0u : SURV_UNSAFE));
-        nsurv += __popc(cmask);
+        const uint32_t smask = __ballot_sync(FULL, near && safe);
+        const uint32_t umask = __ballot_sync(FULL, near && !safe);
+        const uint32_t below = (1u << lane) - 1u;
+        if (near && safe) lst_all[nsafe + __popc(smask & below)] = (uint16_t)((uint32_t)c | code);
+        if (near && !safe)
+          lst_all[SURV_CAP - 1 - (nunsafe + __popc(umask & below))] = (uint16_t)((uint32_t)c | code | SURV_UNSAFE);
+        nsafe += __popc(smask);
+        nunsafe += __popc(umask);
       }
       __syncwarp();
 
@@ -665,6 +672,9 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
       asm volatile("" : "+r"(stg_s));  // opaque: kept in a register, not recomputed per hit
       const uint32_t jacc_s = smem_addr(jacc), jwrap_s = smem_addr(jwrap);
 #endif
+      for (int segment = 0; segment < (PBC == 1 ? 2 : 1); ++segment) {  // safe clusters, then the others
+      const uint16_t* lst = segment == 0 ? lst_all : lst_all + (SURV_CAP - nunsafe);
+      const int nsurv = segment == 0 ? nsafe : nunsafe;
       const int natoms = nsurv * CELL_CLUSTER;
 #if SWEEP_P2
       // Batches of whole hit words (32 staged atoms): `nq` words over `nb` batches, qmin or qmin + 1
@@ -726,7 +736,6 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
                 pj.y = T((double)pj.y - sy);
                 pj.z = T((double)pj.z - sz);
               }
-              unsafe |= (ent & SURV_UNSAFE) != 0u;
             }
             if (SYM) {
 #if SWEEP_P2
@@ -745,7 +754,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           }
           stg[a] = pj;
         }
-        unsafe = PBC == 1 && __any_sync(FULL, unsafe);
+        unsafe = PBC == 1 && segment == 1;
         __syncwarp();
 
         // one pair: energy, i side in registers, j side (SYM) in the shared accumulators
@@ -932,6 +941,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         }
         __syncwarp();  // the staging buffer is rewritten by the next batch
       }
+      }  // segment
       if (GRAD) {
         T4 g;
         g.x = gx;
