@@ -630,8 +630,11 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             const T ext = hi[a] + hjv[a];
             const T gap = fmax(fabs(d) - ext, T(0));
             d2 += gap * gap;
-            // one shift serves every pair of (tile, cluster) iff ext <= L/2 - rc on this axis
-            if (PBC == 1 && ext + rc > half_box[a]) safe = false;
+            // One shift serves every pair of (tile, cluster) that can be in range iff no displacement
+            // exceeds L - rc on this axis: the displacements lie within |d| + ext of zero, those up to
+            // L/2 are minimum images, and those between L/2 and L - rc are out of range under either
+            // image.  (|d| <= L/2, so ext <= L/2 - rc is sufficient whatever d.)
+            if (PBC == 1 && fabs(d) + ext + rc > len[a]) safe = false;
           }
           // clusters made of padding only sit at 1e18: the periodic shift would fold them back
           near = d2 < pc.cutoff2 && cj.x < T(1e17);
