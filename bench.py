@@ -123,38 +123,31 @@ class ClockSampler:
 
 
 def pin_to_gpu_numa_node(device_index: int):
-    """Restrict this process to the host cores nvidia-smi lists as local to the GPU (`nvidia-smi topo
-    -m`, column "CPU Affinity") before any pinned memory is allocated: with one rank per GPU, first
+    """Restrict this process to the host cores NVML lists as local to the GPU
+    (nvmlDeviceGetCpuAffinity) before any pinned memory is allocated: with one rank per GPU, first
     touch then places the staging buffers of the host path on the GPU's own NUMA node instead of
-    wherever torchrun started the rank.  Returns the core list as a string, or None."""
+    wherever torchrun started the rank.  Returns the core list as a string, or None when NVML gives
+    no usable answer -- fewer than four cores that this process may run on is treated as such: a
+    rank squeezed onto one core launches kernels slower than the GPU runs them."""
     try:
-        text = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
-    except (OSError, subprocess.SubprocessError):
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cores = {64 * w + bit for w, word in enumerate(mask) for bit in range(64) if (int(word) >> bit) & 1}
+    except Exception:  # pylint: disable=broad-except
         return None
-    header = next((line for line in text.splitlines() if "CPU Affinity" in line), None)
-    row = next((line for line in text.splitlines() if line.split("\t")[0].strip() == f"GPU{device_index}"), None)
-    if header is None or row is None:
-        return None
-    names = [c.strip() for c in header.split("\t")]
-    cells = [c.strip() for c in row.split("\t")]
-    # the header row has an empty first cell: align from the right-hand columns by name
     try:
-        column = names.index("CPU Affinity")
-        spec = cells[column] if len(cells) == len(names) else cells[column - (len(names) - len(cells))]
-    except (ValueError, IndexError):
-        return None
-    cores = set()
-    try:
-        for part in spec.split(","):
-            lo, _, hi = part.partition("-")
-            cores.update(range(int(lo), int(hi or lo) + 1))
         allowed = cores & os.sched_getaffinity(0)
-        if not allowed:
+        if len(allowed) < 4:
             return None
         os.sched_setaffinity(0, allowed)
     except (ValueError, OSError, AttributeError):
         return None
-    return spec
+    ordered = sorted(allowed)
+    return f"{len(ordered)} cores, {ordered[0]}-{ordered[-1]}"
 
 
 def measured_peaks() -> dict:

@@ -215,8 +215,11 @@ int cvp_evaluate(cvp_cv* cv, int dtype, const void* positions, const void* box, 
                  int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,
                  void* stream);
 
-/* Same through HOST buffers (pinned for full speed): frames are cut in chunks that flow through
- * host->device copy, kernels and device->host copy on separate streams.  Synchronous.            */
+/* Same through HOST buffers (pinned for full speed): frames are cut in chunks (a short first and
+ * last one) that flow through host->device copy, kernels and device->host copy on the streams of
+ * two pipeline slots -- four slots and two workspaces for pair-sum specs, whose consecutive chunks
+ * may run at once.  Staging buffers and workspaces belong to the spec and live until cvp_destroy.
+ * Synchronous.                                                                                   */
 int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
                       int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,
                       int device);

@@ -7,7 +7,8 @@ import cvpack_b200 as cvpack  # noqa: E402
 from scripts import workloads  # noqa: E402
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 device = torch.device("cuda:0")
-cvs, system, x, box, _ = workloads.walkers(frames, 5, device)
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+cvs, system, x, box, _ = workloads.walkers(frames, seed, device)
 cv = cvs["contacts"]
 ctx = cvpack.BatchContext(system, x, box, device=device)
 native = ctx._native_cv(cv)
