@@ -230,10 +230,9 @@ class XTCFile:
         The writer's rounding (integers per nm, usually 1000); 0 for files of at most 9 atoms,
         which are stored uncompressed.
     hasBox
-        Always true: every XTC frame carries box vectors (all zeros when the writer had none).
+        Every XTC frame carries box vectors, all zeros when the writer had none: true when the box
+        of the first frame is not all zeros.
     """
-
-    hasBox = True
 
     def __init__(self, path: t.Union[str, os.PathLike], readThreads: t.Optional[int] = None) -> None:
         self.path = os.fspath(path)
@@ -251,6 +250,7 @@ class XTCFile:
         _native.check(lib.cvp_xtc_info(self._handle, C.byref(frames), C.byref(atoms), C.byref(precision)))
         self.numFrames, self.numAtoms = int(frames.value), int(atoms.value)
         self.precision = float(precision.value)
+        self.hasBox = bool(self.numFrames and self.readFrames(0, 1)[1].any())
 
     def close(self) -> None:
         """Unmap the file."""

@@ -20,3 +20,6 @@ $NCU -k 'regex:rmsd_multi_(cov_mma|gradient_pk)' -s 4 -c 2 -f -o /tmp/multi pyth
 python scripts/ncu_summary.py /tmp/multi.ncu-rep rmsd_multi > $R/${T}_ncu_rmsd_multi_mma.txt
 tail -c 600 $R/${T}_bench_default.json | head -c 300; echo; head -c 400 $R/${T}_bench_reference.json; echo
 grep -c cell_sweep $R/${T}_launches_contacts.csv; head -4 $R/${T}_ncu_cell_sweep_sym.txt; head -4 $R/${T}_ncu_rmsd_fused.txt; head -4 $R/${T}_ncu_rg_fused.txt; head -3 $R/${T}_ncu_rmsd_multi_mma.txt
+python scripts/bench_trajectory.py --frames 512 --chunk 64 > $R/${T}_bench_trajectory.json 2>> $R/${T}_bench_default.err
+python scripts/bench_trajectory.py --frames 512 --chunk 64 --format xtc >> $R/${T}_bench_trajectory.json 2>> $R/${T}_bench_default.err
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $R/${T}_smoke.log 2>&1; tail -1 $R/${T}_smoke.log

@@ -273,6 +273,45 @@ def test_symmetric_sweep_vs_c_oracle(periodic):
     assert (grad2 - grad).abs().max() <= 5e-6 * grad.abs().max()
 
 
+@pytest.mark.parametrize(
+    "n1,n2,n,box,frames",
+    # group sizes that leave ragged chunks and tiles of the dealt layout (CellLayout): one atom past
+    # a chunk, a prime, a group smaller than a tile; the 6.2 nm box with 2 x 2.5k of 23k atoms is
+    # configs[4]: sparse groups, wide tiles, some (tile, cluster) pairs in the per-pair
+    # minimum-image segment; 2.45 nm is barely more than twice the cutoff: most pairs are
+    [(1537, 3089, 6000, 3.92, 3), (2500, 2500, 23000, 6.2, 2), (29, 1901, 2500, 2.93, 3), (700, 800, 1500, 2.45, 3)],
+)
+@pytest.mark.parametrize("path", ["sym", "two_sweeps"])
+def test_sweep_layouts_vs_c_oracle(n1, n2, n, box, frames, path):
+    """Both sweep paths on scattered groups of awkward sizes, against the C oracle."""
+    rng = np.random.default_rng(41)
+    x = lattice_frames(rng, frames, n, box)
+    system = unit_system(n)
+    members = rng.permutation(n)
+    g1, g2 = sorted(members[:n1].tolist()), sorted(members[n1:n1 + n2].tolist())
+    cv = cvpack.NumberOfContacts(g1, g2, plain_nonbonded(n, True), thresholdDistance=0.6)
+    cv.addToSystem(system)
+    ctx = cvpack.BatchContext(system, x, [box] * 3)
+    native = ctx._native_cv(cv)  # pylint: disable=protected-access
+    native.set_option("time_kernels", 1)
+    if path == "sym":
+        native.set_option("nsplit", 1)
+    else:
+        native.set_option("sym", 0)
+    value, grad = cv.getValueAndGradient(ctx)
+    assert native.kernel_time("sweep")[1] == (1 if path == "sym" else 2)
+    assert int(native.stat("last_path")) == (2 if path == "sym" else 1)
+    stored = ctx.getPositions().double().cpu().numpy()
+    ref_value, ref_grad = c_oracle.contacts_batch(stored, g1, g2, (), np.diag([box] * 3), r0=0.6, rc=1.2, rs=0.9)
+    v = value._value.double().cpu().numpy()
+    g = grad.double().cpu().numpy()
+    assert np.abs(v - ref_value).max() <= 1e-5 * np.abs(ref_value).max()
+    assert np.abs(g - ref_grad).max() <= 1e-5 * np.abs(ref_grad).max()
+    assert not g[:, sorted(set(range(n)) - set(g1) - set(g2))].any()
+    value_again, grad_again = cv.getValueAndGradient(ctx)
+    assert torch.equal(value_again._value, value._value) and torch.equal(grad_again, grad)
+
+
 @pytest.mark.parametrize("metric", ["progress", "deviation"])
 @pytest.mark.parametrize(
     "n_group,first,frames,milestones,tail",

@@ -353,6 +353,18 @@ def test_xtc_uncompressed_frame_is_the_documented_byte_layout(tmp_path):
     assert steps.tolist() == [42] and times.tolist() == [8.5]
 
 
+def test_xtc_has_box_only_when_the_writer_had_one(tmp_path):
+    """Every XTC frame has a box record; a file written without boxes holds zeros there and must be
+    streamed as a trajectory without periodic box (it used to reach the context as a zero box)."""
+    rng = np.random.default_rng(23)
+    x = _water_box(rng, 10, 2.0)[None].repeat(3, axis=0)
+    XTCFile.write(tmp_path / "nobox.xtc", x)
+    XTCFile.write(tmp_path / "box.xtc", x, [2.0, 2.0, 2.0])
+    assert XTCFile(tmp_path / "nobox.xtc").hasBox is False
+    assert XTCFile(tmp_path / "nobox.xtc").read(0, 3)[1] is None
+    assert XTCFile(tmp_path / "box.xtc").hasBox is True
+
+
 def test_xtc_compressed_header_fields(tmp_path):
     rng = np.random.default_rng(17)
     x = _water_box(rng, 40, 3.0)[None]
