@@ -418,43 +418,40 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
     for (int j = 0; j < 6; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // loader: a stage is 32 rows (frames for A, groups for B) x 48 values (16 atoms x 3), contiguous
-  // in global memory per row; element e of the stage goes to fragment position
-  //   row r = 3 * (e / 48) + comp, tile r / 8, k-step atom / 4:  ((ks * 12 + r / 8) * 32 + (r % 8) * 4 + atom % 4)
-  constexpr int ROW = MMA_KA * 3;
-  constexpr int NQ = MULTI_TF * ROW / MULTI_THREADS;  // 6
-  static_assert(MULTI_TF * ROW % MULTI_THREADS == 0 && MULTI_TF == MULTI_TG, "loader shape");
+  // in global memory per row.  Thread t takes the 6 consecutive values 6 (t % 8) .. of row t / 8:
+  // atoms 2 (t % 8) and 2 (t % 8) + 1, three components each.  Value (atom a, row r = 3 row + comp)
+  // goes to fragment position ((a / 4) * 12 + r / 8) * 32 + (r % 8) * 4 + a % 4
+  //   = 384 (a / 4) + 4 r + a % 4 = dst + 4 comp + (a odd),
+  // so the whole role of a thread is three numbers (round 2: six offsets, six destinations and
+  // twelve guards per thread pushed the kernel over its 128 registers and the compiler recomputed
+  // them in the main loop -- 82 % of the executed instructions were not DMMA).
+  static_assert(MMA_KA == 16 && MULTI_THREADS == 256 && MULTI_TF == 32 && MULTI_TG == 32, "loader shape");
+  constexpr int NQ = 6;
   float xr[NQ];
   double yr[NQ];
-  const float* x_base = pos + (f0 * num_atoms + first_atom) * 3;
-  const double* y_base = ref + (int64_t)g0 * n * 3;
-  uint32_t x_off[NQ], y_off[NQ];
-  int s_dst[NQ], a_rel_x[NQ], a_rel_y[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const int e = tid + q * MULTI_THREADS;
-    const int row = e / ROW, rest = e - row * ROW;
-    const int a = rest / 3, c = rest - a * 3;
-    const int r = 3 * row + c;
-    s_dst[q] = (((a >> 2) * (MMA_ROWS / 8) + (r >> 3)) << 5) + ((r & 7) << 2) + (a & 3);
-    a_rel_x[q] = f0 + row < num_frames ? a : (1 << 30);
-    a_rel_y[q] = g0 + row < num_groups ? a : (1 << 30);
-    x_off[q] = (uint32_t)row * (uint32_t)(num_atoms * 3) + (uint32_t)rest;
-    y_off[q] = (uint32_t)row * (uint32_t)(n * 3) + (uint32_t)rest;
-  }
+  const int l_row = tid >> 3, l_atom = 2 * (tid & 7);
+  const float* x_src = pos + ((f0 + l_row) * num_atoms + first_atom + l_atom) * 3;
+  const double* y_src = ref + ((int64_t)(g0 + l_row) * n + l_atom) * 3;
+  const int dst = 384 * (l_atom >> 2) + 12 * l_row + (l_atom & 3);
+  // an invalid row (frame or group beyond the end) is encoded as an atom that is never in range
+  const int a_x = f0 + l_row < num_frames ? l_atom : (1 << 30);
+  const int a_y = g0 + l_row < num_groups ? l_atom : (1 << 30);
   auto load_regs = [&](int a0) {
+    const float* xs = x_src + (int64_t)a0 * 3;
+    const double* ys = y_src + (int64_t)a0 * 3;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      xr[q] = a0 + a_rel_x[q] < a_end ? __ldg(x_base + x_off[q] + (int64_t)a0 * 3) : 0.f;
-      yr[q] = a0 + a_rel_y[q] < a_end ? __ldg(y_base + y_off[q] + (int64_t)a0 * 3) : 0.0;
+      xr[q] = a0 + a_x + q / 3 < a_end ? __ldg(xs + q) : 0.f;
+      yr[q] = a0 + a_y + q / 3 < a_end ? __ldg(ys + q) : 0.0;
     }
   };
   auto store_regs = [&](int buf) {
-    double* as = &As[buf][0][0][0];
-    double* bs = &Bs[buf][0][0][0];
+    double* as = &As[buf][0][0][0] + dst;
+    double* bs = &Bs[buf][0][0][0] + dst;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      as[s_dst[q]] = (double)xr[q];
-      bs[s_dst[q]] = yr[q];
+      as[4 * (q % 3) + q / 3] = (double)xr[q];
+      bs[4 * (q % 3) + q / 3] = yr[q];
     }
   };
 
