@@ -753,7 +753,9 @@ struct RmsdCV : cvp_cv {
   // option "multi_mma": FP64 tensor-core (DMMA) versions of the multi kernels; 1 = gradient operands
   // pre-packed in fragment order and fed by TMA, 2 = register-staged gradient, 0 = SIMT DFMA,
   // 3 = like 1 with the covariance operands fed by TMA as well (measured: 0.93 ms against 0.89 ms
-  // for the register-staged covariance kernel -- kept for the record, not the default)
+  // for the register-staged covariance kernel -- kept for the record, not the default).  The
+  // covariance of mode 1 is the three-buffer kernel without block-wide barriers, of modes 2 and 3
+  // (when the rows are not aligned) the double-buffered one.
   int use_multi_mma = 1;
   std::vector<double> ref_pack;  // references in the fragment order of rmsd_multi_gradient_pk_kernel
   std::vector<double> ref_pack_cov;  // ... and of rmsd_multi_cov_pk_kernel
@@ -952,10 +954,16 @@ struct RmsdCV : cvp_cv {
       if (!cov_configured) {
         CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_cov_pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)MULTI_COV_PK_SMEM));
+        CVP_CUDA_CHECK(cudaFuncSetAttribute(rmsd_multi_cov_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)MULTI_COV3_SMEM));
         cov_configured = true;
       }
       timer.begin("rmsd_multi_cov", st);
-      if (use_multi_mma == 3 && bulk_rows)
+      if (use_multi_mma == 1)
+        rmsd_multi_cov_ring_kernel<<<cov_grid, MULTI_THREADS, MULTI_COV3_SMEM, st>>>(
+            reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
+            static_cast<const double*>(d_ref.ptr), num_groups, B, multi_sk, partials);
+      else if (use_multi_mma == 3 && bulk_rows)
         rmsd_multi_cov_pk_kernel<<<cov_grid, MULTI_THREADS, MULTI_COV_PK_SMEM, st>>>(
             reinterpret_cast<const float*>(pos), N, multi_first, multi_n,
             static_cast<const double*>(d_ref_pack_cov.ptr), num_groups, B, multi_sk, partials);

@@ -505,6 +505,138 @@ __global__ void __launch_bounds__(MULTI_THREADS, 2)
 // grid = (frame tiles, atom tiles); dynamic shared memory MULTI_GRAD_MMA_SMEM; two CTAs per SM, so
 // that the prologue (x tile, frame constants) and the epilogue (coalesced rows of the gradient) of
 // one CTA run under the tensor-core loop of the other.
+// ---- covariance, three buffers and no block-wide barrier -------------------------------------------
+// The kernel above ends every stage (16 atoms: 72 DMMA per warp) in __syncthreads(): the warps of a
+// CTA meet, the DMMA pipes of their SM quarters wait for the slowest of them, and with two CTAs per
+// SM nobody else is there to fill in (ncu: the pipe is 79 % busy, top stall math_pipe_throttle --
+// when a warp wants the pipe it is busy, but one fifth of the time nobody wants it).  Same loader,
+// same fragment order, same summation order; but three stage buffers and two mbarriers per buffer
+// arrived on *one stage ahead of the wait*: at the top of stage s a thread stores the values of
+// stage s + 1 (loaded during stage s - 1) and arrives on full[s + 1], loads stage s + 2 into
+// registers, and only then waits for full[s] -- which everybody arrived on a whole stage ago.  The
+// buffer of stage s + 1 was last read in stage s - 2: empty[] is arrived on after the reads and
+// waited on before the stores, again a stage apart.
+constexpr int COV3_BUFS = 3;
+constexpr int COV3_STAGE = (MMA_KA / 4) * (MMA_ROWS / 8) * 32;  // doubles per operand and buffer
+constexpr size_t MULTI_COV3_SMEM = 2 * COV3_BUFS * COV3_STAGE * sizeof(double) + 2 * COV3_BUFS * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(MULTI_THREADS, 2)
+    rmsd_multi_cov_ring_kernel(const float* __restrict__ pos, int64_t num_atoms, int first_atom, int n,
+                               const double* __restrict__ ref /* [G][n][3], centred */, int num_groups,
+                               int64_t num_frames, int SK, double* __restrict__ partials) {
+  extern __shared__ __align__(16) double multi_smem[];
+  double* As = multi_smem;                       // [COV3_BUFS][k-step][tile][32]
+  double* Bs = As + COV3_BUFS * COV3_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(Bs + COV3_BUFS * COV3_STAGE);
+  uint64_t* empty = full + COV3_BUFS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int64_t f0 = (int64_t)blockIdx.x * MULTI_TF;
+  const int g0 = blockIdx.y * MULTI_TG;
+  const int sk = blockIdx.z;
+  const int ns = num_groups * SK;
+  const int chunks_total = (n + MMA_KA - 1) / MMA_KA;
+  const int chunks_per = (chunks_total + SK - 1) / SK;
+  const int a_begin = min(n, sk * chunks_per * MMA_KA);
+  const int a_end = min(n, (sk + 1) * chunks_per * MMA_KA);
+  const int stages = (a_end - a_begin + MMA_KA - 1) / MMA_KA;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < COV3_BUFS; ++k) {
+      mbar_init(&full[k], MULTI_THREADS / 32);
+      mbar_init(&empty[k], MULTI_THREADS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  double acc[3][6][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // (loader roles: see rmsd_multi_cov_mma_kernel)
+  constexpr int NQ = 6;
+  float xr[NQ];
+  double yr[NQ];
+  const int l_row = tid >> 3, l_atom = 2 * (tid & 7);
+  const float* x_src = pos + ((f0 + l_row) * num_atoms + first_atom + l_atom) * 3;
+  const double* y_src = ref + ((int64_t)(g0 + l_row) * n + l_atom) * 3;
+  const int dst = 384 * (l_atom >> 2) + 12 * l_row + (l_atom & 3);
+  const int a_x = f0 + l_row < num_frames ? l_atom : (1 << 30);
+  const int a_y = g0 + l_row < num_groups ? l_atom : (1 << 30);
+  auto load_regs = [&](int a0) {
+    const float* xs = x_src + (int64_t)a0 * 3;
+    const double* ys = y_src + (int64_t)a0 * 3;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      xr[q] = a0 + a_x + q / 3 < a_end ? __ldg(xs + q) : 0.f;
+      yr[q] = a0 + a_y + q / 3 < a_end ? __ldg(ys + q) : 0.0;
+    }
+  };
+  // stage s -> buffer s % 3; its k-th use (k = s / 3) completes phase k of both barriers
+  auto store_stage = [&](int s) {
+    const int buf = s % COV3_BUFS;
+    if (s >= COV3_BUFS) mbar_wait(&empty[buf], (uint32_t)(s / COV3_BUFS - 1) & 1u);  // reads of stage s - 3
+    double* as = As + buf * COV3_STAGE + dst;
+    double* bs = Bs + buf * COV3_STAGE + dst;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      as[4 * (q % 3) + q / 3] = (double)xr[q];
+      bs[4 * (q % 3) + q / 3] = yr[q];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[buf]);
+  };
+
+  if (stages > 0) {
+    load_regs(a_begin);
+    store_stage(0);
+    if (stages > 1) load_regs(a_begin + MMA_KA);
+  }
+  for (int s = 0; s < stages; ++s) {
+    if (s + 1 < stages) store_stage(s + 1);
+    if (s + 2 < stages) load_regs(a_begin + (s + 2) * MMA_KA);
+    const int buf = s % COV3_BUFS;
+    mbar_wait(&full[buf], (uint32_t)(s / COV3_BUFS) & 1u);
+    const double* as = As + buf * COV3_STAGE;
+    const double* bs = Bs + buf * COV3_STAGE;
+#pragma unroll
+    for (int ks = 0; ks < MMA_KA / 4; ++ks) {
+      double a[3], b[6];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) a[i] = as[((ks * (MMA_ROWS / 8) + 3 * wm + i) << 5) + lane];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) b[j] = bs[((ks * (MMA_ROWS / 8) + 6 * wn + j) << 5) + lane];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dmma(acc[i][j], a[i], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[buf]);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int r = 8 * (3 * wm + i) + (lane >> 2);
+    const int64_t f = f0 + r / 3;
+    const int c = r % 3;
+    if (f >= num_frames) continue;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int q = 8 * (6 * wn + j) + 2 * (lane & 3) + h;
+        const int g = g0 + q / 3, d = q % 3;
+        if (g >= num_groups) continue;
+        partials[((size_t)f * ns + (size_t)g * SK + sk) * 13 + 4 + 3 * c + d] = acc[i][j][h];
+      }
+    }
+  }
+}
+
 constexpr int MMA_TA = 64;                     // atoms per CTA tile
 constexpr int MMA_KG = 4;                      // groups per stage
 constexpr int MMA_GSTEPS = MMA_KG * 3 / 4;     // k-steps per stage
