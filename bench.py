@@ -483,6 +483,27 @@ def run_extras(device, sampler, steps, peaks, select=None) -> list:
         seconds, value, grad = oracle_sample(cv, system, sample, box)
         return seconds, value, grad, 1, "NumPy FP64 oracle (oracle/cv_oracle.py), one thread"
 
+    # configs[1], the other CV it names: ResidueCoordination between the two 10k-atom groups
+    if wanted("residue_coordination"):
+        cv, system, x, box, info = workloads.residue_coordination(1024, 2, device)
+        pairs = info["residues"] ** 2
+
+        def coordination_roofline(frames, n, ms, per_step, kernel_ms, steps_, peaks_):
+            # 10^6 centroid pairs x W with p_in = 1 (no cutoff: every pair counts)
+            m, count = kernel_ms.get("sweep", (0.0, 0))
+            flop = frames * pairs * 60.0
+            achieved = steps_ * flop / (m * 1e-3) / 1e12 if count else None
+            return {"bound": "fp32", "kernel": "centroid pair sweep", "achieved": achieved, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None, "traffic": None,
+                    "launches": count, "kernel_share_of_step": m / (ms * steps_) if count else None,
+                    "algorithmic_gflop_per_frame": flop / frames / 1e9}
+
+        records.append(extra_record("residue_coordination", "configs[1]", cv, system, x, box, sampler,
+                                    max(steps, 10), peaks, kernels=("sweep",), roofline_fn=coordination_roofline,
+                                    cpu_fn=numpy_oracle, cpu_frames=2))
+        del cv, system, x
+        torch.cuda.empty_cache()
+
     # configs[2]: streaming RMSD / Rg on 100k atoms
     for name, builder, kernels, cpu in (
         ("rmsd", workloads.rmsd, ("rmsd_sums", "rmsd_gradient", "rmsd_fused"), c_rmsd),

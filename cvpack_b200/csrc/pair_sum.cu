@@ -55,7 +55,7 @@ __global__ void pack_groups_kernel(const T* __restrict__ pos, int64_t num_atoms,
 }
 
 // ---- 2/3. sweep --------------------------------------------------------------------------------
-template <typename T, int KIND, int PBC, bool OVERLAP, bool GRAD>
+template <typename T, int KIND, int PBC, bool OVERLAP, bool GRAD, bool FAST6 = false>
 __global__ void __launch_bounds__(PAIR_THREADS)
     pair_sweep_kernel(const typename Vec4<T>::type* __restrict__ ipos,
                       const typename Vec4<T>::type* __restrict__ jpos,
@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(PAIR_THREADS)
               min_image<PBC>(ex, ey, ez, bd);
             }
             Fn::eval_d(pc, ex, ey, ez, fc, e, coef);
+          } else if constexpr (FAST6) {
+            contacts_rational6(pc, r2, e[0], coef);  // 1/(1+x^6): r^2 only, no square root
           } else
             Fn::eval(pc, r2, prmi[k], qj, fc, e, coef);
 #pragma unroll
@@ -1092,12 +1094,18 @@ struct CentroidPairSumCV : cvp_cv {
         n2, p1, p2, total);
     CVP_LAUNCH_CHECK();
     const unsigned grid1 = (unsigned)(B * nb1), grid2 = (unsigned)(B * nb2);
+    // the default step function 1/(1+x^6) has a pair function that needs r^2 only
+    const bool fast6 = d.step_kind == CVP_STEP_RATIONAL && (int)d.step_p0 == 6;
+    auto value_kernel = fast6 ? pair_sweep_kernel<T, KIND, PBC, false, false, true>
+                              : pair_sweep_kernel<T, KIND, PBC, false, false, false>;
+    auto grad_kernel = fast6 ? pair_sweep_kernel<T, KIND, PBC, false, true, true>
+                             : pair_sweep_kernel<T, KIND, PBC, false, true, false>;
     timer.begin("sweep", st);
     if (need_grad)
-      pair_sweep_kernel<T, KIND, PBC, false, true><<<grid1, PAIR_THREADS, 0, st>>>(
+      grad_kernel<<<grid1, PAIR_THREADS, 0, st>>>(
           p1, p2, nullptr, nullptr, n1, n2, nb1, box, a.box_mode, pc, nullptr, partials, gr1);
     else
-      pair_sweep_kernel<T, KIND, PBC, false, false><<<grid1, PAIR_THREADS, 0, st>>>(
+      value_kernel<<<grid1, PAIR_THREADS, 0, st>>>(
           p1, p2, nullptr, nullptr, n1, n2, nb1, box, a.box_mode, pc, nullptr, partials, nullptr);
     timer.end(st);
     CVP_LAUNCH_CHECK();
@@ -1106,7 +1114,7 @@ struct CentroidPairSumCV : cvp_cv {
     CVP_LAUNCH_CHECK();
     if (!need_grad) return CVP_OK;
     timer.begin("sweep", st);
-    pair_sweep_kernel<T, KIND, PBC, false, true><<<grid2, PAIR_THREADS, 0, st>>>(
+    grad_kernel<<<grid2, PAIR_THREADS, 0, st>>>(
         p2, p1, nullptr, nullptr, n2, n1, nb2, box, a.box_mode, pc, nullptr, nullptr, gr2);
     timer.end(st);
     CVP_LAUNCH_CHECK();

@@ -18,6 +18,8 @@ import cvpack_b200 as cvpack
 CONFIGS = {
     "contacts": "NumberOfContacts 10k x 10k atoms, cubic PBC L=5.844 nm, r0=0.6 rc=1.2 rs=0.9 nm, "
     "4096 frames/GPU of water density (100 atoms/nm^3)",
+    "residue_coordination": "ResidueCoordination between two groups of 1000 residues x 10 atoms (the 10k + 10k "
+    "atoms of the contact workload), r0=1.0 nm, PBC, weighByMass=False, same frames",
     "rmsd": "RMSD (quaternion alignment) of a 100k-atom synthetic protein, 2048 frames",
     "rg": "RadiusOfGyration of a 100k-atom synthetic protein, 2048 frames",
     "path": "PathInRMSDSpace (progress), 64 milestones x 20k atoms, sigma 0.05 nm, 1024 frames",
@@ -104,6 +106,29 @@ def contacts(num_frames: int, seed: int, device, num_atoms: int = 20000, box: fl
     )
     cv.addToSystem(system)
     return cv, system, x, [box] * 3, {"lattice": lattice, "r0": r0, "box": box}
+
+
+def residue_coordination(num_frames: int, seed: int, device, num_atoms: int = 20000, box: float = 5.844,
+                         residue_size: int = 10):
+    """configs[1], SURVEY 8(d) variant: every 10 consecutive atoms are a residue; coordination between
+    the residues of the first and of the second half (1000 x 1000 centroid pairs, no cutoff)."""
+    from cvpack_b200 import app
+
+    x, lattice = lattice_frames(num_frames, num_atoms, box, seed, device)
+    system = unit_system(num_atoms)
+    topology = app.Topology()
+    chain = topology.addChain()
+    residues = []
+    for _ in range(num_atoms // residue_size):
+        residue = topology.addResidue("ALA", chain)
+        for k in range(residue_size):
+            topology.addAtom(f"C{k}", app.Element.getBySymbol("C"), residue)
+        residues.append(residue)
+    half = len(residues) // 2
+    cv = cvpack.ResidueCoordination(residues[:half], residues[half:], pbc=True, thresholdDistance=1.0,
+                                    weighByMass=False, includeHydrogens=True)
+    cv.addToSystem(system)
+    return cv, system, x, [box] * 3, {"lattice": lattice, "residues": half}
 
 
 def rmsd(num_frames: int, seed: int, device, num_atoms: int = 100000):
