@@ -22,7 +22,7 @@ CAPTURES = {
                    ["stream_fused.cuh", "rmsd.cu", "common.cuh"]),
     "gyration_fused": ("r2_ncu_rg_fused.txt", "stream_fused_kernel", 2048,
                        ["stream_fused.cuh", "gyration.cu", "common.cuh"]),
-    "rmsd_multi_cov": ("r2_ncu_rmsd_multi_mma.txt", "rmsd_multi_cov_mma_kernel", 1024,
+    "rmsd_multi_cov": ("r2_ncu_rmsd_multi_mma.txt", "rmsd_multi_cov_ring_kernel", 1024,
                        ["rmsd_multi.cuh", "rmsd.cu", "common.cuh"]),
     "rmsd_multi_gradient": ("r2_ncu_rmsd_multi_mma.txt", "rmsd_multi_gradient_pk_kernel", 1024,
                             ["rmsd_multi.cuh", "rmsd.cu", "common.cuh"]),

@@ -16,7 +16,7 @@ $NCU -k regex:stream_fused_kernel -s 2 -c 1 -f -o /tmp/rmsd python scripts/profi
 python scripts/ncu_summary.py /tmp/rmsd.ncu-rep stream_fused > $R/${T}_ncu_rmsd_fused.txt
 $NCU -k regex:stream_fused_kernel -s 2 -c 1 -f -o /tmp/rg python scripts/profile_fused.py rg 2048 > $R/ncu_rg.log 2>&1
 python scripts/ncu_summary.py /tmp/rg.ncu-rep stream_fused > $R/${T}_ncu_rg_fused.txt
-$NCU -k 'regex:rmsd_multi_(cov_mma|gradient_pk)' -s 4 -c 2 -f -o /tmp/multi python scripts/bench_path.py 1024 1 > $R/ncu_multi.log 2>&1
+$NCU -k 'regex:rmsd_multi_(cov_ring|gradient_pk)' -s 4 -c 2 -f -o /tmp/multi python scripts/bench_path.py 1024 1 > $R/ncu_multi.log 2>&1
 python scripts/ncu_summary.py /tmp/multi.ncu-rep rmsd_multi > $R/${T}_ncu_rmsd_multi_mma.txt
 tail -c 600 $R/${T}_bench_default.json | head -c 300; echo; head -c 400 $R/${T}_bench_reference.json; echo
 grep -c cell_sweep $R/${T}_launches_contacts.csv; head -4 $R/${T}_ncu_cell_sweep_sym.txt; head -4 $R/${T}_ncu_rmsd_fused.txt; head -4 $R/${T}_ncu_rg_fused.txt; head -3 $R/${T}_ncu_rmsd_multi_mma.txt

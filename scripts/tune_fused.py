@@ -1,16 +1,16 @@
 """Sweep the sub-slice size and lag of the fused streaming kernel (RMSD / Rg, 100k atoms, 2048 frames)."""
 import sys, torch
 sys.path.insert(0, ".")
-import bench, cvpack_b200 as cvpack
+import cvpack_b200 as cvpack
+from scripts import workloads
 which = sys.argv[1] if len(sys.argv) > 1 else "rmsd"
 subs = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 lags = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [3]
 slots_list = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
 hints_list = [int(v) for v in sys.argv[5].split(",")] if len(sys.argv) > 5 else [3]
-spec = bench.WORKLOADS[which]
+spec = {"frames": 2048, "atoms": 100000}
 dev = torch.device("cuda:0")
-x, ref = bench.make_positions(which, spec, spec["frames"], 100, device=dev)
-cv, system = bench.build_cv(which, spec, ref)
+cv, system, x, _, _ = (workloads.rmsd if which == "rmsd" else workloads.gyration)(spec["frames"], 3, dev)
 ctx = cvpack.BatchContext(system, x, None, device=dev)
 nat = ctx._native_cv(cv)
 value = torch.empty(spec["frames"], device=dev); grad = torch.empty_like(x)
