@@ -43,29 +43,16 @@ constexpr int CELL_MAX_CELLS = CELL_MAX_AXIS * CELL_MAX_AXIS * CELL_MAX_AXIS;
 #endif
 constexpr int CELL_SWEEP_THREADS = CELL_SWEEP_THREADS_VALUE;
 constexpr int CELL_SMEM_BUDGET = 64 * 1024;  // bytes of j data per CTA (2 CTAs per SM)
-// Phase 2 of the sweep (SWEEP_P2): 0 = hit masks in registers, stage and accumulators through
-// generic pointers (round-2 start); 1 = hit masks in a per-warp shared array (a lane that runs out of
-// bits fetches its next word with one load instead of a select chain over four registers) and
-// explicit 32-bit shared addresses for the staged atom and the j accumulators
-#ifndef SWEEP_P2
-#define SWEEP_P2 1
-#endif
-// Phase 1 (SWEEP_SQ, FP32 only): the staged record is (-2 x_j, |x_j|^2) and the test reads
+// Phase 2 of the sweep keeps the hit masks in a per-warp shared array (a lane that runs out of bits
+// fetches its next word with one load) and addresses the staged atoms and the j accumulators through
+// explicit 32-bit shared addresses.
+// Phase 1 in FP32 (SQ in the kernel): the staged record is (-2 x_j, |x_j|^2) and the test reads
 // |x_j|^2 - 2 x_i . x_j < rc^2 - |x_i|^2 + margin: three FMAs and a compare per pair instead of three
 // subtractions, three multiply-adds and a compare.  A conservative filter (the margin covers the
 // cancellation), phase 2 forms the exact x_j - x_i = fma(-0.5, -2 x_j, -x_i) and tests r^2 < rc^2
 // again.  The tag (or accumulator address) of a staged atom moves to a side array.
-#ifndef SWEEP_ATOM_STRIDE
-#define SWEEP_ATOM_STRIDE 1
-#endif
-#ifndef SWEEP_SQ
-#define SWEEP_SQ SWEEP_P2
-#endif
-#if SWEEP_SQ && !SWEEP_P2
-#error "SWEEP_SQ needs SWEEP_P2"
-#endif
 #ifndef CELL_SMEM_BUDGET_SYM_KB
-#define CELL_SMEM_BUDGET_SYM_KB (SWEEP_SQ ? 55 : SWEEP_P2 ? 63 : 72)
+#define CELL_SMEM_BUDGET_SYM_KB 55
 #endif
 constexpr int CELL_SMEM_BUDGET_SYM = CELL_SMEM_BUDGET_SYM_KB * 1024;  // ... with the j gradient accumulators
 constexpr int TAG_DUMMY = -1;
@@ -372,8 +359,8 @@ __host__ __device__ inline size_t cell_sweep_smem(bool sym = false) {
                        (size_t)(CELL_SWEEP_THREADS / 32) * batch_atoms) +
          (size_t)(CELL_SWEEP_THREADS / 32) * SURV_CAP * sizeof(uint16_t) +
          (sym ? (size_t)jchunk * 4 * sizeof(int) : 0) +
-         (SWEEP_P2 ? (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms / 32) * 32 * sizeof(uint32_t) : 0) +
-         (SWEEP_SQ && sizeof(T) == 4 ? (size_t)(CELL_SWEEP_THREADS / 32) * batch_atoms * sizeof(int) : 0);
+         (size_t)(CELL_SWEEP_THREADS / 32) * (batch_atoms / 32) * 32 * sizeof(uint32_t) +  // hit words
+         (sizeof(T) == 4 ? (size_t)(CELL_SWEEP_THREADS / 32) * batch_atoms * sizeof(int) : 0);  // tags (SQ)
 }
 
 // Symmetric mode: exact fixed-point accumulation.  x = round(v * scale) (F2I, |v * scale| < 2^30 by
@@ -382,39 +369,10 @@ __host__ __device__ inline size_t cell_sweep_smem(bool sym = false) {
 // +-1 into the wrap counter of that component.  Three 10-bit counters, biased by 512, share one word
 // per atom: |wraps| <= scale * max|dE/dr| * n_i / 2^32 < 500 is part of the host's choice of scale.
 constexpr int SYM_WRAP_INIT = 512 | (512 << 10) | (512 << 20);
-#ifndef SYM_VARIANT
-#define SYM_VARIANT 0
-#endif
 __device__ __forceinline__ unsigned sym_fixed(float v, float scale) {
-#if SYM_VARIANT == 1 || SYM_VARIANT == 3
-  // |v * scale| < 2^22: the integer sits in the mantissa of v * scale + 1.5 * 2^23 (FMA pipe only)
-  return (unsigned)(__float_as_int(fmaf(v, scale, 12582912.0f)) - 0x4B400000);
-#else
   return (unsigned)__float2int_rn(v * scale);
-#endif
 }
-__device__ __forceinline__ void sym_add3(int* lo, int* wraps, float vx, float vy, float vz, float scale) {
-  const unsigned x0 = sym_fixed(vx, scale), x1 = sym_fixed(vy, scale), x2 = sym_fixed(vz, scale);
-  unsigned* acc = reinterpret_cast<unsigned*>(lo);
-#if SYM_VARIANT >= 2
-  atomicAdd(acc, x0);
-  atomicAdd(acc + 1, x1);
-  atomicAdd(acc + 2, x2);
-#else
-  const unsigned o0 = atomicAdd(acc, x0), o1 = atomicAdd(acc + 1, x1), o2 = atomicAdd(acc + 2, x2);
-  const unsigned n0 = o0 + x0, n1 = o1 + x1, n2 = o2 + x2;
-  // signed overflow of a component: old and addend have the same sign, the new value the other one
-  const unsigned f0 = (o0 ^ n0) & (x0 ^ n0), f1 = (o1 ^ n1) & (x1 ^ n1), f2 = (o2 ^ n2) & (x2 ^ n2);
-  if ((int)(f0 | f1 | f2) < 0) {  // rare: one branch for the three components
-    int bump = 0;
-    if ((int)f0 < 0) bump += (int)x0 < 0 ? -1 : 1;
-    if ((int)f1 < 0) bump += ((int)x1 < 0 ? -1 : 1) << 10;
-    if ((int)f2 < 0) bump += ((int)x2 < 0 ? -1 : 1) << 20;
-    atomicAdd(wraps, bump);
-  }
-#endif
-}
-// the same through 32-bit shared-window addresses (acc = &lo[0], wraps = &wrap word)
+// (acc: 32-bit shared-window address of the atom's three sums; the wrap word is found from it)
 __device__ __forceinline__ unsigned atoms_add(uint32_t addr, unsigned x) {
   unsigned old;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(x) : "memory");
@@ -482,12 +440,12 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
   T4* jsm = reinterpret_cast<T4*>(sweep_smem);
   T4* bsm = jsm + jchunk;  // cluster boxes of the chunk: (centre, half) pairs
   // [NWARP] staging areas: BATCH_ATOMS records, then (SQ) BATCH_ATOMS tags
-  constexpr bool SQ = SWEEP_SQ && sizeof(T) == 4;
+  constexpr bool SQ = sizeof(T) == 4;
   constexpr int STAGE_BYTES = BATCH_ATOMS * (int)sizeof(T4) + (SQ ? BATCH_ATOMS * 4 : 0);
   unsigned char* stage_all = reinterpret_cast<unsigned char*>(bsm + (jchunk / CELL_CLUSTER) * 2);
   T4* survivors_all = reinterpret_cast<T4*>(stage_all + NWARP * STAGE_BYTES);  // [NWARP][SURV_CAP] 16-bit entries
-  uint32_t* hits_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(survivors_all) + NWARP * SURV_CAP);  // SWEEP_P2: [NWARP][NW][32]
-  int* jacc = reinterpret_cast<int*>(hits_all + (SWEEP_P2 ? NWARP * NW * 32 : 0));  // SYM: [jchunk][3] wrapping sums
+  uint32_t* hits_all = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(survivors_all) + NWARP * SURV_CAP);  // [NWARP][NW][32]
+  int* jacc = reinterpret_cast<int*>(hits_all + NWARP * NW * 32);  // SYM: [jchunk][3] wrapping sums
   int* jwrap = jacc + 3 * jchunk;                                  // SYM: [jchunk] packed wrap counters
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -651,15 +609,14 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
       __syncwarp();
 
       // ---- batches ----
-      // A *batch* = BATCH_CL surviving clusters (128 atoms in FP32) copied -- already shifted to the
-      // right periodic image -- into this warp's staging buffer.  Phase 1 tests every staged atom
-      // against the lane's i atom and records hits in NW 32-bit masks; phase 2 lets every lane walk
-      // its own hits, so the expensive pair function runs for real contacts only and the j side is
-      // accumulated in shared memory.  Phase 2 lasts as long as its busiest lane: batch `b` of `nb`
-      // takes survivors b, b + nb, b + 2 nb, ... -- a sample of the whole neighbourhood of the tile
-      // instead of one corner of it -- so that every lane finds about the same number of hits in
-      // every batch (a batch of 16 *consecutive* clusters lies on one side of the tile: the lanes
-      // on that side had 2.3 x the average number of hits, ncu: 14 of 32 lanes active).
+      // A *batch* = up to NW hit words of 32 staged atoms (128 atoms in FP32), copied -- already
+      // shifted to the right periodic image -- into this warp's staging buffer.  Phase 1 tests every
+      // staged atom against the lane's i atom and records hits in the hit words; phase 2 lets every
+      // lane walk its own hits, so the expensive pair function runs for real contacts only and the
+      // j side is accumulated in shared memory.  Phase 2 lasts as long as its busiest lane, so a
+      // batch is a sample of the tile's whole neighbourhood (see the striding below), not one corner
+      // of it: a batch of 16 *consecutive* clusters lies on one side of the tile, and the lanes on
+      // that side had 2.3 x the average number of hits (ncu: 14 of 32 lanes active).
       T4* stg = reinterpret_cast<T4*>(stage_all + warp * STAGE_BYTES);
       int* side = reinterpret_cast<int*>(stg + BATCH_ATOMS);
       // SQ: what |x_j|^2 - 2 x_i . x_j is compared with.  Every quantity of a pair in range is at
@@ -670,16 +627,13 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         const T xi2 = fma(pi.z, pi.z, fma(pi.y, pi.y, pi.x * pi.x));
         sq_thr = (pc.cutoff2 - xi2) + T(7.62939453125e-6) * (xi2 + pc.cutoff2);
       }
-#if SWEEP_P2
       uint32_t stg_s = smem_addr(stg);
       asm volatile("" : "+r"(stg_s));  // opaque: kept in a register, not recomputed per hit
       const uint32_t jacc_s = smem_addr(jacc), jwrap_s = smem_addr(jwrap);
-#endif
       for (int segment = 0; segment < (PBC == 1 ? 2 : 1); ++segment) {  // safe clusters, then the others
       const uint16_t* lst = segment == 0 ? lst_all : lst_all + (SURV_CAP - nunsafe);
       const int nsurv = segment == 0 ? nsafe : nunsafe;
       const int natoms = nsurv * CELL_CLUSTER;
-#if SWEEP_P2
       // Batches of whole hit words (32 staged atoms): `nq` words over `nb` batches, qmin or qmin + 1
       // each, so that phase 1 tests no word of padding.  The sample is strided by *atom*: number the
       // atoms of the surviving clusters t = 8 survivor + atom; slot a of batch b is atom b + a nb
@@ -692,28 +646,13 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
       const int nb = (nq + NW - 1) / NW;
       const int qmin = nb > 0 ? nq / nb : 0;
       const int strided = 32 * qmin * nb;
-#else
-      const int nb = (nsurv + BATCH_CL - 1) / BATCH_CL;
-#endif
       for (int bi = 0; bi < nb; ++bi) {
-#if SWEEP_P2
         const int words = qmin + (bi < nq - qmin * nb ? 1 : 0);  // <= NW
         const int take = 4 * words;                               // clusters, padding included
-#if SWEEP_ATOM_STRIDE
         auto slot_atom = [&](int a) { return a < 32 * qmin ? bi + a * nb : strided + 32 * bi + (a - 32 * qmin); };
-#else
-        auto slot_atom = [&](int a) {  // strided by cluster
-          const int e = a >> 3;
-          return (e < 4 * qmin ? bi + e * nb : (strided >> 3) + 4 * bi + (e - 4 * qmin)) * CELL_CLUSTER + (a & 7);
-        };
-#endif
-#else
-        const int take = (nsurv - bi + nb - 1) / nb;  // <= BATCH_CL
-        auto slot_atom = [&](int a) { return (bi + (a >> 3) * nb) * CELL_CLUSTER + (a & 7); };
-#endif
-        bool unsafe = false;
+        bool unsafe = false;  // (set below: the segment decides)
         // (words that phase 1 does not test need no padding)
-        for (int a = lane; a < (SWEEP_P2 ? take * CELL_CLUSTER : BATCH_ATOMS); a += 32) {
+        for (int a = lane; a < take * CELL_CLUSTER; a += 32) {
           T4 pj;
           pj.x = pj.y = pj.z = T(1e18);  // padding of a short batch: never in range
           pj.w = tag_encode(TAG_DUMMY, T(0));
@@ -741,13 +680,8 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               }
             }
             if (SYM) {
-#if SWEEP_P2
               // the shared-window address of the atom's accumulators (-1: padding)
               pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : (int)(jacc_s + (uint32_t)(cl * CELL_CLUSTER + (t & 7)) * 12u), T(0));
-#else
-              // the accumulator slot of the atom within the chunk (-1: padding)
-              pj.w = tag_encode(tag_decode(pj.w) < 0 ? -1 : cl * CELL_CLUSTER + (t & 7), T(0));
-#endif
             }
           }
           if constexpr (SQ) {
@@ -780,7 +714,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           Acc e[NCH];
           T coef;
           if constexpr (FAST6) {
-            contacts_rational6<T, SYM && SWEEP_P2>(pc, r2, e[0], coef);
+            contacts_rational6<T, SYM>(pc, r2, e[0], coef);
           } else if constexpr (KIND == CVP_PAIR_SOFTMIN) {
             Fn::eval_d(pc, ex[0], ex[1], ex[2], fc, e, coef);
           } else {
@@ -797,11 +731,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
             gy -= fy;
             gz -= fz;
             if constexpr (SYM) {
-#if SWEEP_P2
               sym_add3_s((uint32_t)tagj, jacc_s, jwrap_s, (float)fx, (float)fy, (float)fz, sym_scale);
-#else
-              sym_add3(jacc + tagj * 3, jwrap + tagj, (float)fx, (float)fy, (float)fz, sym_scale);
-#endif
             }
           }
         };
@@ -842,7 +772,6 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
           }
         } else {
           // phase 1: bit positions are compile-time constants
-#if SWEEP_P2
           uint32_t* hw = hits_all + warp * (NW * 32) + lane;  // word w of this lane at hw[32 w]
           int mine = 0;
           // its 32-bit shared address, kept opaque so that it lives in a register instead of being
@@ -895,52 +824,6 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
               }
             }
           }
-#else
-          uint32_t hits[NW];
-#pragma unroll
-          for (int w = 0; w < NW; ++w) {
-            uint32_t m = 0u;
-#pragma unroll
-            for (int u = 0; u < 32; ++u) {
-              const T4 pj = stg[w * 32 + u];
-              const T dx = pj.x - pr.x, dy = pj.y - pr.y, dz = pj.z - pr.z;
-              if (fma(dz, dz, fma(dy, dy, dx * dx)) < pc.cutoff2) m |= 1u << u;
-            }
-            hits[w] = m;
-          }
-          int mine = 0;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) mine += __popc(hits[w]);
-          const int rounds = __reduce_max_sync(FULL, mine);
-          // phase 2: every lane walks its own hit bits through a working copy `cur` of one mask
-          // word; the next non-empty word is fetched (select chain, no dynamic register indexing)
-          // only when `cur` runs out.  Lanes start at different words, so that neighbouring i atoms
-          // (similar hit lists) do not reach the same j accumulator in the same instruction.
-          static_assert((NW & (NW - 1)) == 0, "NW must be a power of two");
-          int wsel = lane & (NW - 1);
-          uint32_t cur = 0u;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) {
-            if (wsel == w) cur = hits[w];
-          }
-          for (int it = 0; it < rounds; ++it) {
-            if (it < mine) {
-              while (cur == 0u) {
-                wsel = (wsel + 1) & (NW - 1);
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                  if (wsel == w) cur = hits[w];
-                }
-              }
-              const int k = wsel * 32 + __ffs(cur) - 1;
-              cur &= cur - 1u;
-              const T4 pj = stg[k];
-              double ex[3] = {0.0, 0.0, 0.0};
-              if constexpr (KIND == CVP_PAIR_SOFTMIN) exact_displacement(k, ex);
-              interact(tag_decode(pj.w), pj.x - pr.x, pj.y - pr.y, pj.z - pr.z, false, ex);
-            }
-          }
-#endif
         }
         __syncwarp();  // the staging buffer is rewritten by the next batch
       }

@@ -523,11 +523,7 @@ struct PairSumCV : cvp_cv {
       return false;
     const double slope = contacts6_max_slope();
     if (!(slope > 0)) return false;
-#if SYM_VARIANT == 1 || SYM_VARIANT == 3
-    const double single = 4194304.0 / slope;  // magic-number conversion: |v * scale| < 2^22
-#else
     const double single = 1073741824.0 / slope;
-#endif
     const double limit = std::min({67108864.0, single,
                                    500.0 * 4294967296.0 / (slope * cell_round_up(ni_pad, CELL_TILE))});
     const int exponent = (int)std::floor(std::log2(limit * 0.999));
