@@ -406,6 +406,18 @@ __device__ __forceinline__ float sym_value(int lo, int wraps, int component, flo
   return (float)(((double)carry * 4294967296.0 + (double)lo) * (double)inv_scale);
 }
 
+// Where the symmetric sweep leaves its gradients: with `grad` set, straight in the caller's
+// [B][N][3] array (every atom of the two disjoint groups is written exactly once: the i atoms when
+// their tile has seen the last chunk, the j atoms when their chunk is flushed), scaled, added when
+// `accumulate`; the packed arrays and the scatter pass are then not needed.
+template <typename T>
+struct DirectGradient {
+  T* grad = nullptr;
+  int64_t num_atoms = 0;
+  T scale = T(1);
+  int accumulate = 0;
+};
+
 // grid = B * nsplit CTAs; CTA (b, part) owns the i tiles part, part + nsplit, ... (strided by warp).
 template <typename T, int KIND, int PBC, bool OVERLAP, bool GRAD, bool FAST6, bool SYM = false>
 __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
@@ -418,7 +430,7 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
                       double* __restrict__ energy_partials,
                       typename Vec4<T>::type* __restrict__ igrad,
                       typename Vec4<T>::type* __restrict__ jgrad, float sym_scale, int sym_passes,
-                      int jchunk_atoms, int i_nchunk) {
+                      int jchunk_atoms, int i_nchunk, DirectGradient<T> direct) {
   static_assert(!SYM || (GRAD && !OVERLAP && sizeof(T) == 4 && !PairFn<T, KIND>::HAS_PARAMS),
                 "symmetric mode: FP32 gradients of disjoint groups without per-atom parameters");
   using T4 = typename Vec4<T>::type;
@@ -834,7 +846,17 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         g.y = gy;
         g.z = gz;
         g.w = T(0);
-        ig[ipos] = g;
+        if (SYM && direct.grad != nullptr && j0 + jchunk_atoms >= nj_pad) {
+          if (tagi >= 0) {
+            T* out = direct.grad + (b * direct.num_atoms + (tagi & TAG_INDEX_MASK)) * 3;
+            const bool add = direct.accumulate != 0;
+            out[0] = (add ? out[0] : T(0)) + direct.scale * gx;
+            out[1] = (add ? out[1] : T(0)) + direct.scale * gy;
+            out[2] = (add ? out[2] : T(0)) + direct.scale * gz;
+          }
+        } else {
+          ig[ipos] = g;
+        }
       }
     }
     if (SYM) {
@@ -850,13 +872,24 @@ __global__ void __launch_bounds__(CELL_SWEEP_THREADS, 2)
         g.y = T(sym_value(jacc[3 * a + 1], wraps, 1, inv_scale));
         g.z = T(sym_value(jacc[3 * a + 2], wraps, 2, inv_scale));
         g.w = T(0);
-        if (tile_first > 0) {
-          const T4 old = jg[a];
-          g.x += old.x;
-          g.y += old.y;
-          g.z += old.z;
+        if (direct.grad != nullptr) {
+          const int tag = tag_decode(jsm[a].w);
+          if (tag >= 0) {
+            T* out = direct.grad + (b * direct.num_atoms + (tag & TAG_INDEX_MASK)) * 3;
+            const bool add = direct.accumulate != 0 || tile_first > 0;
+            out[0] = (add ? out[0] : T(0)) + direct.scale * g.x;
+            out[1] = (add ? out[1] : T(0)) + direct.scale * g.y;
+            out[2] = (add ? out[2] : T(0)) + direct.scale * g.z;
+          }
+        } else {
+          if (tile_first > 0) {
+            const T4 old = jg[a];
+            g.x += old.x;
+            g.y += old.y;
+            g.z += old.z;
+          }
+          jg[a] = g;
         }
-        jg[a] = g;
         jacc[3 * a] = jacc[3 * a + 1] = jacc[3 * a + 2] = 0;
         jwrap[a] = SYM_WRAP_INIT;
       }

@@ -610,6 +610,16 @@ struct PairSumCV : cvp_cv {
       CVP_LAUNCH_CHECK();
     }
     last_path = sym ? 2 : 1;
+    // the symmetric sweep writes its gradients where they belong (no packed arrays, no scatter pass)
+    const T gscale = KIND == CVP_PAIR_SOFTMIN ? T(1) : (T)d.scale;
+    DirectGradient<T> direct;
+    if (sym) {
+      direct.grad = grad;
+      direct.num_atoms = N;
+      direct.scale = gscale;
+      direct.accumulate = accumulate ? 1 : 0;
+      if (!accumulate) CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
+    }
     auto sweep = [&](bool first, bool with_grad, const Acc* coef, double* energy) -> int {
       const T4* ip = first ? s1 : s2;
       const T4* jp = first ? s2 : s1;
@@ -641,7 +651,8 @@ struct PairSumCV : cvp_cv {
       timer.begin("sweep", st);
       kernel<<<(unsigned)(B * nsplit), CELL_SWEEP_THREADS, sweep_smem, st>>>(
           ip, jp, jb, prm_atom, nip, njp, nsplit, box, a.box_mode, pc, coef, energy,
-          with_grad ? out : nullptr, jout, sym_scale, sym_passes, jlay.cpc * CELL_CLUSTER, ilay.nchunk);
+          with_grad ? out : nullptr, jout, sym_scale, sym_passes, jlay.cpc * CELL_CLUSTER, ilay.nchunk,
+          jout != nullptr ? direct : DirectGradient<T>{});
       timer.end(st);
       CVP_LAUNCH_CHECK();
       return CVP_OK;
@@ -665,10 +676,8 @@ struct PairSumCV : cvp_cv {
     }
     if (!need_grad) return CVP_OK;
     if (!sym && (status = sweep(false, true, frame_coef, nullptr)) != CVP_OK) return status;
-    if (!accumulate)
-      CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
-    const T gscale = KIND == CVP_PAIR_SOFTMIN ? T(1) : (T)d.scale;
-    {
+    if (!sym) {
+      if (!accumulate) CVP_CUDA_CHECK(cudaMemsetAsync(grad, 0, (size_t)B * N * 3 * sizeof(T), st));
       int64_t total = B * (int64_t)n1p;
       int blocks = (int)std::min<int64_t>(div_up(total, 256), 148 * 16);
       cell_scatter_kernel<T><<<blocks, 256, 0, st>>>(s1, gr1, n1p, N, gscale, grad, total);
