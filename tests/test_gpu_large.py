@@ -310,6 +310,20 @@ def test_sweep_layouts_vs_c_oracle(n1, n2, n, box, frames, path):
     assert not g[:, sorted(set(range(n)) - set(g1) - set(g2))].any()
     value_again, grad_again = cv.getValueAndGradient(ctx)
     assert torch.equal(value_again._value, value._value) and torch.equal(grad_again, grad)
+    # CVP_FLAG_ACCUMULATE through the raw C ABI (the symmetric sweep adds its gradients in place)
+    from cvpack_b200 import _native  # pylint: disable=import-outside-toplevel
+
+    pos = ctx.getPositions()
+    box9 = torch.tensor(np.diag([box] * 3).ravel(), dtype=torch.float32, device=pos.device)
+    base_value = torch.full_like(value._value, 0.25)
+    base_grad = torch.full_like(grad, -0.5)
+    acc_value, acc_grad = base_value.clone(), base_grad.clone()
+    native.evaluate(_native.CVP_F32, pos.data_ptr(), box9.data_ptr(), _native.CVP_BOX_SHARED, frames, n,
+                    acc_value.data_ptr(), acc_grad.data_ptr(), _native.CVP_FLAG_ACCUMULATE,
+                    torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.allclose(acc_value, base_value + value._value, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(acc_grad, base_grad + grad, rtol=0, atol=1e-6 * float(grad.abs().max()) + 1e-7)
 
 
 @pytest.mark.parametrize("metric", ["progress", "deviation"])
