@@ -229,6 +229,7 @@ SYMBOLS: t.Dict[str, t.Tuple[t.Any, t.List[t.Any]]] = {
     "cvp_version": (C.c_int, []),
     "cvp_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cvp_launch_count": (C.c_int64, []),
+    "cvp_host_chunks": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32)]),
     "cvp_set_workspace_limit": (C.c_int, [_vp, C.c_int64]),
     "cvp_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "cvp_get_stat": (C.c_int, [_vp, C.c_char_p, _f64p]),

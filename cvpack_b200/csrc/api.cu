@@ -174,6 +174,28 @@ int cvp_evaluate(cvp_cv* cv, int dtype, const void* positions, const void* box, 
 }  // extern "C"
 
 namespace {
+// Chunks of the host path: at most ~256 MiB of coordinates each, at least 1 frame, and >= 4 chunks
+// when possible.  The first copy in and the last copy out overlap nothing: a short first and a short
+// last chunk (a quarter of a chunk, but a whole number of 148-frame waves so that the kernels take
+// the same path as for the long chunks) shorten both; the frames in between go in equal chunks.
+std::vector<int64_t> host_chunks(int64_t num_frames, size_t frame_bytes) {
+  std::vector<int64_t> sizes;
+  if (num_frames <= 0) return sizes;
+  int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t(256) << 20) / std::max<size_t>(frame_bytes, 1)));
+  chunk = std::min(chunk, std::max<int64_t>(1, (num_frames + 3) / 4));
+  const int64_t edge = (chunk / 4 + 147) / 148 * 148;
+  if (chunk >= 592 && num_frames >= 2 * edge + chunk) {
+    const int64_t rest = num_frames - 2 * edge;
+    const int64_t middle = (rest + chunk - 1) / chunk;
+    sizes.push_back(edge);
+    for (int64_t m = 0; m < middle; ++m) sizes.push_back(rest / middle + (m < rest % middle ? 1 : 0));
+    sizes.push_back(edge);
+  } else {
+    for (int64_t first = 0; first < num_frames; first += chunk) sizes.push_back(std::min(chunk, num_frames - first));
+  }
+  return sizes;
+}
+
 // Host-buffer path: frames flow through H2D copy -> kernels -> D2H copy in chunks; two slots so the
 // copies of one chunk overlap the kernels of the other (copy engines in both directions + SMs).
 // With `masses` (host, double [N]) the effective mass of every frame is computed on the device
@@ -192,25 +214,8 @@ int evaluate_host_impl(cvp_cv* cv, int dtype, const void* positions, const void*
   const bool copy_grad = grad != nullptr;
   const bool need_grad = copy_grad || emass != nullptr;
   const size_t frame_bytes = (size_t)num_atoms * 3 * es;
-  // chunk: at most ~256 MiB of coordinates, at least 1 frame, and >= 4 chunks when possible
-  int64_t chunk = std::max<int64_t>(1, (int64_t)((size_t(256) << 20) / frame_bytes));
-  chunk = std::min(chunk, std::max<int64_t>(1, (num_frames + 3) / 4));
-  // The first copy in and the last copy out overlap nothing: a short first and a short last chunk
-  // (a quarter of a chunk, but a whole number of 148-frame waves so that the kernels take the same
-  // path as for the long chunks) shorten both; the frames in between go in equal chunks.
-  std::vector<int64_t> sizes;
-  {
-    const int64_t edge = (chunk / 4 + 147) / 148 * 148;
-    if (chunk >= 592 && num_frames >= 2 * edge + chunk) {
-      const int64_t rest = num_frames - 2 * edge;
-      const int64_t middle = (rest + chunk - 1) / chunk;
-      sizes.push_back(edge);
-      for (int64_t m = 0; m < middle; ++m) sizes.push_back(rest / middle + (m < rest % middle ? 1 : 0));
-      sizes.push_back(edge);
-    } else {
-      for (int64_t first = 0; first < num_frames; first += chunk) sizes.push_back(std::min(chunk, num_frames - first));
-    }
-  }
+  const std::vector<int64_t> sizes = host_chunks(num_frames, frame_bytes);
+  const int64_t chunk = *std::max_element(sizes.begin(), sizes.end());
   // Pipeline slots (staging buffers + stream): two, so that the copies of one chunk overlap the
   // kernels of the other.  A spec that can run twice at once (concurrent_runs(): two workspaces)
   // gets four: the kernels of chunks i and i + 1 overlap -- the tail of a launch, when SMs run out
@@ -374,6 +379,16 @@ int evaluate_host_impl(cvp_cv* cv, int dtype, const void* positions, const void*
 }  // namespace
 
 extern "C" {
+
+int cvp_host_chunks(int64_t num_frames, int64_t frame_bytes, int64_t* sizes, int32_t capacity,
+                    int32_t* count) {
+  CVP_REQUIRE(num_frames >= 0 && frame_bytes > 0 && count != nullptr, "invalid argument");
+  const std::vector<int64_t> plan = host_chunks(num_frames, (size_t)frame_bytes);
+  *count = (int32_t)plan.size();
+  if (sizes != nullptr)
+    for (int32_t k = 0; k < std::min<int32_t>(capacity, *count); ++k) sizes[k] = plan[k];
+  return CVP_OK;
+}
 
 int cvp_evaluate_host(cvp_cv* cv, int dtype, const void* positions, const void* box, int box_mode,
                       int64_t num_frames, int64_t num_atoms, void* value, void* grad, int flags,

@@ -377,6 +377,10 @@ int cvp_version(void);
 int cvp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 /* Kernels launched by this library since the process started (all threads).                     */
 int64_t cvp_launch_count(void);
+/* The chunks cvp_evaluate_host cuts a batch into (frames per chunk, in order), for callers that
+ * want to size pinned buffers or progress bars: `sizes` may be NULL to query `count` only.       */
+int cvp_host_chunks(int64_t num_frames, int64_t frame_bytes, int64_t* sizes, int32_t capacity,
+                    int32_t* count);
 /* Bytes of per-spec device workspace a spec may use per evaluate call (default 4 GiB).           */
 int cvp_set_workspace_limit(cvp_cv* cv, int64_t bytes);
 /* Per-family tuning switch (meaning documented in DESIGN.md); returns previous value.            */

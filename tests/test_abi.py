@@ -116,3 +116,34 @@ def test_evaluate_without_device_fails_loudly():
         cv.evaluate(_native.CVP_F32, pos.ctypes.data, None, 0, 1, 3, out.ctypes.data, None, 0, 0)
     sm = ctypes.c_int()
     assert _native.load().cvp_device_info(0, ctypes.byref(sm), None, None) != 0
+
+
+@pytest.mark.parametrize(
+    "frames,frame_bytes",
+    [(4096, 240000), (2048, 1200000), (1, 12), (7, 10**9), (1184, 240000), (100000, 1200), (593, 240000)],
+)
+def test_host_chunk_schedule(frames, frame_bytes):
+    """cvp_host_chunks: the chunks of cvp_evaluate_host cover the batch in order, none above 256 MiB
+    of coordinates (or one frame), at least four when there are four frames; with long chunks the
+    first and the last are short -- whole 148-frame waves -- and the ones in between are equal."""
+    lib = _native.load()
+    count = ctypes.c_int32()
+    assert lib.cvp_host_chunks(frames, frame_bytes, None, 0, ctypes.byref(count)) == 0
+    sizes = (ctypes.c_int64 * count.value)()
+    assert lib.cvp_host_chunks(frames, frame_bytes, sizes, count.value, ctypes.byref(count)) == 0
+    sizes = list(sizes)
+    assert sum(sizes) == frames and all(s >= 1 for s in sizes)
+    assert all(s == 1 or s * frame_bytes <= 256 << 20 for s in sizes)
+    assert len(sizes) >= min(frames, 4)
+    if len(sizes) >= 3 and sizes[0] < max(sizes):  # tapered
+        assert sizes[0] == sizes[-1] and sizes[0] % 148 == 0
+        middle = sizes[1:-1]
+        assert max(middle) - min(middle) <= 1 and sizes[0] <= min(middle)
+
+
+def test_host_chunk_schedule_of_the_headline_batch():
+    lib = _native.load()
+    count = ctypes.c_int32()
+    sizes = (ctypes.c_int64 * 16)()
+    assert lib.cvp_host_chunks(4096, 240000, sizes, 16, ctypes.byref(count)) == 0
+    assert list(sizes)[: count.value] == [296, 876, 876, 876, 876, 296]
